@@ -1,0 +1,397 @@
+// gemm_dq.cu -- K1: fused block-dequant GEMM on tcgen05 tensor cores (sm_100a).
+//
+// Replaces ggml_compute_forward_mul_mat + vec_dot_q*_q8_* (reference: ggml/src/ggml.c:11223-11437,
+// 2333-3624) for every weight GEMM of the ViT / text transformer (clip.cpp:1080-1137, 1360-1417).
+//
+//   Y[token, feature] = sum_k X[token, k] * W[feature, k]  (+ bias, + epilogue)
+//
+// computed "swap-AB": the WEIGHT tile is the UMMA A operand (M = 128 features = TMEM lanes), the
+// ACTIVATION tile is the B operand (N = 256 tokens = TMEM columns).  Consequences:
+//   * only 128x64 weights are unpacked per 128x256x64 MMA block (half the ALU work of the other
+//     orientation), and bias / Q-scale are per-thread constants in the epilogue;
+//   * the epilogue thread <-> feature mapping makes every global store naturally coalesced
+//     (32 lanes = 32 consecutive features of one token), no shared-memory transpose needed.
+//
+// Warp roles (persistent CTA, 1 per SM, 512 threads; 256 for unquantized f16 weights):
+//   warp 0      TMA producer: activation box [256 x 64] (UTMALDG, 128B swizzle) + ONE bulk copy (UBLKCP) of the
+//               packed 32-weight blocks + scales of the [128 x 64] weight tile (wpack.h)       -> in_full[s]
+//   warps 8-15  unpack: packed q4_0/q4_1/q5_0/q5_1/q8_0 blocks -> fp16/bf16 A tile in the UMMA
+//               K-major/128B-swizzle layout (st.shared.v4, conflict-free)                        -> w_full[j]
+//   warp 1      one thread issues tcgen05.mma (M128 N256 K16, kind::f16), fp32 accumulators in TMEM,
+//               tcgen05.commit releases input stages / signals the epilogue
+//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / scale / GELU / residual -> coalesced global stores;
+//               double-buffered accumulators (2 x 256 TMEM columns) overlap it with the next tile's MMAs
+//   warp 2      TMEM alloc / dealloc
+//
+// Algorithmic bytes per launch: packed W once + X once + Y once; FLOPs = 2*M*N*K.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm.h"
+#include "wpack.h"
+
+namespace cb {
+
+namespace {
+
+constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
+constexpr int X_STAGE = BN * BK * 2;   // 32768 B
+constexpr int W_STAGE = BM * BK * 2;   // 16384 B
+constexpr int SI = 4;                  // input ring depth (activation box + packed weights)
+constexpr int SW = 3;                  // unpacked-weight ring depth
+constexpr int N_UNPACK_WARPS = 8;
+constexpr int N_EPI_WARPS = 4;
+constexpr uint32_t TMEM_COLS = 512;    // 2 accumulator stages x 256 columns
+
+__host__ __device__ constexpr uint32_t chunk_bytes(int qt) {
+    return qt == 2 ? 4608u : qt == 3 ? 5120u : qt == 6 ? 5632u : qt == 7 ? 6144u : qt == 8 ? 8704u : 0u;
+}
+__host__ __device__ constexpr uint32_t chunk_pad(int qt) { return (chunk_bytes(qt) + 1023u) & ~1023u; }
+__host__ __device__ constexpr uint32_t in_stage_bytes(int qt) { return X_STAGE + (qt == 1 ? (uint32_t)W_STAGE : chunk_pad(qt)); }
+__host__ __device__ constexpr uint32_t smem_bytes(int qt) {
+    return SI * in_stage_bytes(qt) + (qt == 1 ? 0u : (uint32_t)(SW * W_STAGE)) + 256u /*barriers*/ + 1024u /*align slack*/;
+}
+
+struct KParams {
+    CUtensorMap tm_x;
+    CUtensorMap tm_w;
+    const uint8_t* w_packed;
+    const float* bias;
+    void* out;
+    int M, N, K, ldo;
+    int epi, out_bf16, scale_cols;
+    float scale;
+};
+
+CB_DEVINL uint4 lds128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+CB_DEVINL void sts128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+}
+CB_DEVINL uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// Unpack the 32-weight ggml block owned by thread t (= half*128 + row) of a [128 x 64] tile into the
+// UMMA A-operand image: row r at (r/8)*1024 + (r%8)*128, 16-byte chunk c at position c ^ (r%8).
+// Arithmetic matches dequantize_row_q* (ggml/src/ggml.c:1496-1606): (q - zero) * d  or  q * d + m, with the
+// integer part exact (magic-number int->float) and ONE rounding of the product to the operand type.
+template <int QT, bool BF>
+CB_DEVINL void unpack_block(const uint8_t* __restrict__ q, uint8_t* __restrict__ w, int t) {
+    using P = P2<BF>;
+    const int half = t >> 7, r = t & 127, sw = r & 7;
+    uint8_t* row = w + (r >> 3) * 1024 + sw * 128;
+    if constexpr (QT == QT_Q8_0) {
+        const uint4 qa = lds128(q + 16 * t), qb = lds128(q + 4096 + 16 * t);
+        const uint32_t d2 = P::splat_from_f16bits(*reinterpret_cast<const uint16_t*>(q + 8192 + 2 * t));
+        const uint32_t words[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        #pragma unroll
+        for (int c = 0; c < 4; c++) {
+            uint32_t v[4];
+            #pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t s = words[2 * c + h] ^ 0x80808080u;          // int8 -> biased 0..255
+                const uint32_t p01 = prmt(s, 0u, 0x4140u), p23 = prmt(s, 0u, 0x4342u);   // bytes -> 16-bit lanes
+                if constexpr (!BF) {   // fp16: 1024 + s is exact, minus 1152 = signed quant
+                    v[2 * h + 0] = P::mul(P::sub(p01 | P::MAGIC, 0x64806480u), d2);
+                    v[2 * h + 1] = P::mul(P::sub(p23 | P::MAGIC, 0x64806480u), d2);
+                } else {               // bf16 has 7 mantissa bits: 128 + (s & 127), minus 128 or 256 by bit 7
+                    const uint32_t m01 = (p01 & 0x007f007fu) | P::MAGIC, c01 = (p01 & 0x00800080u) ^ 0x43804380u;
+                    const uint32_t m23 = (p23 & 0x007f007fu) | P::MAGIC, c23 = (p23 & 0x00800080u) ^ 0x43804380u;
+                    v[2 * h + 0] = P::mul(P::sub(m01, c01), d2);
+                    v[2 * h + 1] = P::mul(P::sub(m23, c23), d2);
+                }
+            }
+            sts128(row + (((4 * half + c) ^ sw) << 4), v[0], v[1], v[2], v[3]);
+        }
+    } else {
+        constexpr bool Q5 = (QT == QT_Q5_0 || QT == QT_Q5_1);
+        constexpr bool AFFINE = (QT == QT_Q4_1 || QT == QT_Q5_1);
+        const uint4 qs = lds128(q + 16 * t);
+        uint32_t hq = 0;
+        uint32_t off = 4096;
+        if constexpr (Q5) { hq = *reinterpret_cast<const uint32_t*>(q + off + 4 * t); off += 1024; }
+        uint32_t d2, m2 = 0;
+        if constexpr (AFFINE) {
+            const uint32_t dm = *reinterpret_cast<const uint32_t*>(q + off + 4 * t);
+            d2 = P::splat_from_f16bits((uint16_t)(dm & 0xffffu));
+            m2 = P::splat_from_f16bits((uint16_t)(dm >> 16));
+        } else {
+            d2 = P::splat_from_f16bits(*reinterpret_cast<const uint16_t*>(q + off + 2 * t));
+        }
+        // zero point folded into the exact integer subtraction: 8 (q4_0), 16 (q5_0), 0 (q4_1 / q5_1)
+        constexpr uint32_t ZP = (QT == QT_Q4_0) ? 8u : (QT == QT_Q5_0) ? 16u : 0u;
+        constexpr uint32_t C2 = P::MAGIC + (ZP | (ZP << 16));
+        const uint32_t words[4] = {qs.x, qs.y, qs.z, qs.w};
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t v[4];
+            #pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t x = ((words[j] >> (4 * i)) & 0x000f000fu) | P::MAGIC;
+                if constexpr (Q5) {
+                    constexpr int dummy = 0; (void)dummy;
+                    const int sh = 4 * j + i;   // 5th bits of this pair sit at bits sh and sh+16 -> move to bits 4 / 20
+                    const uint32_t hb = (sh >= 4) ? (hq >> (sh - 4)) : (hq << (4 - sh));
+                    x |= hb & 0x00100010u;
+                }
+                const uint32_t qv = P::sub(x, C2);
+                v[i] = AFFINE ? P::fma(qv, d2, m2) : P::mul(qv, d2);
+            }
+            sts128(row + (((4 * half + j) ^ sw) << 4), v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+template <int QT, bool BF>
+__global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(const __grid_constant__ KParams p) {
+    constexpr bool DQ = (QT != QT_F16);
+    constexpr uint32_t CHUNK = chunk_bytes(QT);
+    constexpr uint32_t IN_STAGE = in_stage_bytes(QT);
+    constexpr uint32_t W_RING = SI * IN_STAGE;                         // only for DQ
+    constexpr uint32_t BAR_OFF = SI * IN_STAGE + (DQ ? SW * W_STAGE : 0);
+    constexpr uint32_t IDESC = umma_idesc(BF, BM, BN);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bars = smem_base + BAR_OFF;
+    // barrier slots (8 B each)
+    const uint32_t in_full = bars, in_empty = bars + 8 * SI, w_full = bars + 16 * SI, w_empty = w_full + 8 * SW,
+                   acc_full = w_empty + 8 * SW, acc_empty = acc_full + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * SI + 16 * SW + 32);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SI; i++) {
+            mbar_init(in_full + 8 * i, 1);
+            mbar_init(in_empty + 8 * i, DQ ? 1 + N_UNPACK_WARPS : 1);
+        }
+        for (int i = 0; i < SW; i++) {
+            mbar_init(w_full + 8 * i, N_UNPACK_WARPS);
+            mbar_init(w_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(acc_full + 8 * i, 1);
+            mbar_init(acc_empty + 8 * i, N_EPI_WARPS);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&p.tm_x);
+        if (!DQ) tma_prefetch_desc(&p.tm_w);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_ft = p.N / BM, n_tt = (p.M + BN - 1) / BN, n_tiles = n_ft * n_tt, nkb = p.K / BK;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        uint32_t s = 0, ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int ft = tile % n_ft, tt = tile / n_ft;
+            for (int kb = 0; kb < nkb; kb++) {
+                mbar_wait(in_empty + 8 * s, ph ^ 1);
+                if (lane == 0) {
+                    const uint32_t dst = smem_base + s * IN_STAGE;
+                    if constexpr (DQ) {
+                        mbar_arrive_expect_tx(in_full + 8 * s, X_STAGE + CHUNK);
+                        tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, in_full + 8 * s);
+                        bulk_load_1d(dst + X_STAGE, p.w_packed + ((size_t)ft * nkb + kb) * CHUNK, CHUNK, in_full + 8 * s);
+                    } else {
+                        mbar_arrive_expect_tx(in_full + 8 * s, X_STAGE + W_STAGE);
+                        tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, in_full + 8 * s);
+                        tma_load_2d(dst + X_STAGE, &p.tm_w, kb * BK, ft * BM, in_full + 8 * s);
+                    }
+                }
+                __syncwarp();
+                if (++s == SI) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        uint32_t s = 0, ph = 0, ws = 0, wph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            mbar_wait(acc_empty + 8 * as, aph ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; kb++) {
+                mbar_wait(in_full + 8 * s, ph);
+                if constexpr (DQ) mbar_wait(w_full + 8 * ws, wph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t xa = smem_base + s * IN_STAGE;
+                    const uint32_t wa = DQ ? (smem_base + W_RING + ws * W_STAGE) : (xa + X_STAGE);
+                    const uint64_t da = umma_desc_k128(wa), db = umma_desc_k128(xa);
+                    #pragma unroll
+                    for (int k = 0; k < BK / 16; k++)   // advance 16 elements = 32 B = 2 descriptor units
+                        umma_f16(tmem_base + as * BN, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(in_empty + 8 * s);
+                    if constexpr (DQ) umma_commit(w_empty + 8 * ws);
+                    if (kb == nkb - 1) umma_commit(acc_full + 8 * as);
+                }
+                __syncwarp();
+                if (++s == SI) { s = 0; ph ^= 1; }
+                if constexpr (DQ) { if (++ws == SW) { ws = 0; wph ^= 1; } }
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------------------------ epilogue
+        const int fr = (warp & 3) * 32 + lane;                     // feature row of the tile == TMEM lane
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const int ft = tile % n_ft, tt = tile / n_ft;
+            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            const int n = ft * BM + fr;
+            const float bias = p.bias ? p.bias[n] : 0.0f;
+            const float mul = (n < p.scale_cols) ? p.scale : 1.0f;
+            mbar_wait(acc_full + 8 * as, aph);
+            tc_fence_after();
+            const int tok0 = tt * BN;
+            #pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                if (tok0 + c * 32 >= p.M) break;                  // warp-uniform
+                uint32_t r[32];
+                tmem_ld_32x32(lane_addr + as * BN + c * 32, r);
+                tmem_ld_wait();
+                const int tbase = tok0 + c * 32;
+                const int nvalid = min(32, p.M - tbase);
+                if (p.epi == EPI_RESID32) {
+                    float* o = reinterpret_cast<float*>(p.out) + (size_t)tbase * p.ldo + n;
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (j < nvalid) o[(size_t)j * p.ldo] += __uint_as_float(r[j]) + bias;
+                } else if (p.epi == EPI_STORE32) {
+                    float* o = reinterpret_cast<float*>(p.out) + (size_t)tbase * p.ldo + n;
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (j < nvalid) o[(size_t)j * p.ldo] = __uint_as_float(r[j]) + bias;
+                } else {
+                    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + (size_t)tbase * p.ldo + n;
+                    #pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        float v = __uint_as_float(r[j]) + bias;
+                        if (p.epi == EPI_GELU16) v = gelu_tanh(v);
+                        else if (p.epi == EPI_QGELU16) v = gelu_quick(v);
+                        else v *= mul;
+                        const uint16_t h = p.out_bf16 ? P2<true>::from_float(v) : P2<false>::from_float(v);
+                        if (j < nvalid) o[(size_t)j * p.ldo] = h;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+        }
+    } else if (DQ && warp >= 8) {
+        // ------------------------------------------------------------------ unpack warps
+        const int t = threadIdx.x - 256;
+        uint32_t s = 0, ph = 0, ws = 0, wph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nkb; kb++) {
+                mbar_wait(in_full + 8 * s, ph);
+                mbar_wait(w_empty + 8 * ws, wph ^ 1);
+                unpack_block<DQ ? QT : QT_Q4_0, BF>(smem + s * IN_STAGE + X_STAGE, smem + W_RING + ws * W_STAGE, t);
+                fence_proxy_async_smem();      // st.shared (generic proxy) -> visible to UMMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(w_full + 8 * ws);
+                    mbar_arrive(in_empty + 8 * s);
+                }
+                if (++s == SI) { s = 0; ph ^= 1; }
+                if (++ws == SW) { ws = 0; wph ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+template <int QT, bool BF>
+cudaError_t launch_t(const KParams& kp, int grid, cudaStream_t st) {
+    gemm_dq_kernel<QT, BF><<<grid, QT == QT_F16 ? 256 : 512, smem_bytes(QT), st>>>(kp);
+    return cudaGetLastError();
+}
+template <int QT, bool BF>
+cudaError_t set_attr() {
+    return cudaFuncSetAttribute(gemm_dq_kernel<QT, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(QT));
+}
+
+}  // namespace
+
+bool make_tma_2d_16bit(TmaMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                       uint32_t box_rows) {
+    static_assert(sizeof(CUtensorMap) == sizeof(TmaMap), "CUtensorMap size");
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {row_stride_elems * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(gptr), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+cudaError_t gemm_init() {
+    cudaError_t e;
+    if ((e = set_attr<QT_F16, false>()) != cudaSuccess) return e;
+#define CB_SET(QT)                                                  \
+    if ((e = set_attr<QT, false>()) != cudaSuccess) return e;      \
+    if ((e = set_attr<QT, true>()) != cudaSuccess) return e;
+    CB_SET(QT_Q4_0) CB_SET(QT_Q4_1) CB_SET(QT_Q5_0) CB_SET(QT_Q5_1) CB_SET(QT_Q8_0)
+#undef CB_SET
+    return cudaSuccess;
+}
+
+cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream, int num_sms, uint64_t* launches) {
+    if (a.M <= 0) return cudaSuccess;
+    if (a.N % BM || a.K % BK || !a.x_map || !a.out) return cudaErrorInvalidValue;
+    if (a.qtype == QT_F16 && (a.operand_bf16 || !a.w_map)) return cudaErrorInvalidValue;
+    if (a.qtype != QT_F16 && !a.w_packed) return cudaErrorInvalidValue;
+    KParams kp;
+    memcpy(&kp.tm_x, a.x_map, sizeof(CUtensorMap));
+    if (a.w_map) memcpy(&kp.tm_w, a.w_map, sizeof(CUtensorMap));
+    else memset(&kp.tm_w, 0, sizeof(CUtensorMap));
+    kp.w_packed = a.w_packed;
+    kp.bias = a.bias;
+    kp.out = a.out;
+    kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.ldo = a.ldo;
+    kp.epi = a.epi; kp.out_bf16 = a.out_bf16; kp.scale_cols = a.scale_cols; kp.scale = a.scale;
+    const int n_tiles = (a.N / BM) * ((a.M + BN - 1) / BN);
+    const int grid = n_tiles < num_sms ? n_tiles : num_sms;
+    if (launches) ++*launches;
+    switch (a.qtype) {
+    case QT_F16: return launch_t<QT_F16, false>(kp, grid, stream);
+#define CB_CASE(QT) case QT: return a.operand_bf16 ? launch_t<QT, true>(kp, grid, stream) : launch_t<QT, false>(kp, grid, stream);
+    CB_CASE(QT_Q4_0) CB_CASE(QT_Q4_1) CB_CASE(QT_Q5_0) CB_CASE(QT_Q5_1) CB_CASE(QT_Q8_0)
+#undef CB_CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace cb

@@ -1,0 +1,425 @@
+// host_ops.cpp -- CPU-side members of the clip.h interface.  These are the callers / data formats on either side of
+// the GPU hot path; they are written from the reference's documented behaviour,
+// not from its code, and each function cites the lines whose results it must reproduce.
+#include "host_ops.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+
+#include "gguf.hpp"
+
+namespace cb {
+
+// ---------------------------------------------------------------------------------------------------
+// fp16 <-> fp32 (IEEE binary16, round-to-nearest-even; equals the F16C conversions the reference uses on x86,
+// ggml/src/ggml.c:326-333)
+// ---------------------------------------------------------------------------------------------------
+float f16_to_f32(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp = (h >> 10) & 0x1Fu, man = h & 0x3FFu, bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {   // subnormal: normalise
+            int e = -1;
+            do { e++; man <<= 1; } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3FFu) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7F800000u | (man << 13);
+    else bits = sign | ((exp + 112u) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
+uint16_t f32_to_f16(float f) {
+    uint32_t x;
+    memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7FFFFFFFu;
+    if (x >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | ((x > 0x7F800000u) ? 0x200u : 0u));   // inf / nan
+    if (x >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);                                        // overflow -> inf
+    if (x < 0x33000001u) return (uint16_t)sign;                                                     // underflow -> 0
+    uint32_t exp = x >> 23, man = x & 0x7FFFFFu;
+    if (exp < 113) {   // subnormal half
+        man |= 0x800000u;
+        const uint32_t shift = 126 - exp;           // 14..24
+        const uint32_t half = man >> shift, rem = man & ((1u << shift) - 1), mid = 1u << (shift - 1);
+        uint32_t r = half;
+        if (rem > mid || (rem == mid && (half & 1))) r++;
+        return (uint16_t)(sign | r);
+    }
+    uint32_t r = ((exp - 112) << 10) | (man >> 13);
+    const uint32_t rem = man & 0x1FFFu;
+    if (rem > 0x1000u || (rem == 0x1000u && (r & 1))) r++;   // may carry into the exponent: still correct
+    return (uint16_t)(sign | r);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// block (de)quantisation, ggml/src/ggml.c:866-911 layouts
+// ---------------------------------------------------------------------------------------------------
+bool dequant_row(int qt, const uint8_t* src, float* dst, int64_t k) {
+    if (qt == 0) { memcpy(dst, src, (size_t)k * 4); return true; }
+    if (qt == 1) { for (int64_t i = 0; i < k; i++) { uint16_t h; memcpy(&h, src + 2 * i, 2); dst[i] = f16_to_f32(h); } return true; }
+    const size_t bb = ggml_type_block_bytes(qt);
+    if (!bb || qt < 2 || k % 32) return false;
+    for (int64_t b = 0; b < k / 32; b++) {
+        const uint8_t* p = src + b * bb;
+        float* y = dst + b * 32;
+        uint16_t dh; memcpy(&dh, p, 2);
+        const float d = f16_to_f32(dh);
+        if (qt == 8) { for (int j = 0; j < 32; j++) y[j] = (float)((const int8_t*)(p + 2))[j] * d; continue; }
+        float m = 0.f; uint32_t qh = 0; const uint8_t* qs;
+        if (qt == 2) qs = p + 2;
+        else if (qt == 3) { uint16_t mh; memcpy(&mh, p + 2, 2); m = f16_to_f32(mh); qs = p + 4; }
+        else if (qt == 6) { memcpy(&qh, p + 2, 4); qs = p + 6; }
+        else { uint16_t mh; memcpy(&mh, p + 2, 2); m = f16_to_f32(mh); memcpy(&qh, p + 4, 4); qs = p + 8; }
+        for (int j = 0; j < 16; j++) {
+            int q0 = qs[j] & 0x0F, q1 = qs[j] >> 4;
+            if (qt == 6 || qt == 7) { q0 |= ((qh >> j) & 1) << 4; q1 |= ((qh >> (j + 16)) & 1) << 4; }
+            if (qt == 2) { q0 -= 8; q1 -= 8; }
+            if (qt == 6) { q0 -= 16; q1 -= 16; }
+            if (qt == 3 || qt == 7) { y[j] = (float)q0 * d + m; y[j + 16] = (float)q1 * d + m; }
+            else { y[j] = (float)q0 * d; y[j + 16] = (float)q1 * d; }
+        }
+    }
+    return true;
+}
+
+bool quant_row(int qt, const float* x, uint8_t* dst, int64_t k) {
+    const size_t bb = ggml_type_block_bytes(qt);
+    if (!bb || qt < 2 || k % 32) return false;
+    for (int64_t b = 0; b < k / 32; b++) {
+        const float* xb = x + b * 32;
+        uint8_t* p = dst + b * bb;
+        if (qt == 8) {                                        // ggml.c:1097-1114
+            float amax = 0.f;
+            for (int j = 0; j < 32; j++) amax = std::max(amax, fabsf(xb[j]));
+            const float d = amax / 127.0f, id = d ? 1.0f / d : 0.0f;
+            const uint16_t dh = f32_to_f16(d); memcpy(p, &dh, 2);
+            for (int j = 0; j < 32; j++) ((int8_t*)(p + 2))[j] = (int8_t)roundf(xb[j] * id);
+            continue;
+        }
+        const bool sym = (qt == 2 || qt == 6);
+        const int bits5 = (qt == 6 || qt == 7);
+        float d, mn = 0.f, off;
+        if (sym) {                                            // ggml.c:922-947, 1004-1036: signed abs-max
+            float amax = 0.f, mx = 0.f;
+            for (int j = 0; j < 32; j++) { const float v = xb[j]; if (amax < fabsf(v)) { amax = fabsf(v); mx = v; } }
+            d = mx / (bits5 ? -16.0f : -8.0f);
+            off = bits5 ? 16.5f : 8.5f;
+        } else {                                              // ggml.c:963-988, 1052-1084: min/max
+            float mx = -FLT_MAX; mn = FLT_MAX;
+            for (int j = 0; j < 32; j++) { const float v = xb[j]; if (v < mn) mn = v; if (v > mx) mx = v; }
+            d = (mx - mn) / (bits5 ? 31.0f : 15.0f);
+            off = 0.5f;
+        }
+        const float id = d ? 1.0f / d : 0.0f;
+        const uint16_t dh = f32_to_f16(d); memcpy(p, &dh, 2);
+        uint8_t* qs = p + 2;
+        if (!sym) { const uint16_t mh = f32_to_f16(mn); memcpy(p + 2, &mh, 2); qs += 2; }
+        uint8_t* qhp = qs;
+        if (bits5) qs += 4;
+        uint32_t qh = 0;
+        for (int j = 0; j < 16; j++) {
+            uint8_t q0, q1;
+            if (sym) {
+                // x*id + 8.5f is ONE fused multiply-add in the reference binary: ggml is built with FMA enabled
+                // (CLIP_NATIVE / -mfma) and GCC contracts the expression (ggml.c:937-941, 1020-1024)
+                const int lim = bits5 ? 31 : 15;
+                q0 = (uint8_t)std::min(lim, (int)(int8_t)fmaf(xb[j], id, off));
+                q1 = (uint8_t)std::min(lim, (int)(int8_t)fmaf(xb[j + 16], id, off));
+            } else {
+                const float x0 = (xb[j] - mn) * id, x1 = (xb[j + 16] - mn) * id;
+                if (qt == 7) { q0 = (uint8_t)(x0 + off); q1 = (uint8_t)(x1 + off); }   // no clamp (ggml.c:1074-1075)
+                else { q0 = (uint8_t)std::min(15, (int)(int8_t)(x0 + off)); q1 = (uint8_t)std::min(15, (int)(int8_t)(x1 + off)); }
+            }
+            qs[j] = (uint8_t)((q0 & 0x0F) | ((q1 & 0x0F) << 4));
+            qh |= (uint32_t)((q0 >> 4) & 1) << j;
+            qh |= (uint32_t)((q1 >> 4) & 1) << (j + 16);
+        }
+        if (bits5) memcpy(qhp, &qh, 4);
+    }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tokenizer: clip.cpp:598-679.  The reference splits with the std::regex
+//   's|'t|'re|'ve|'m|'ll|'d| ?[[:alpha:]]+| ?[[:digit:]]+| ?[^\s[:alpha:][:digit:]]+|\s+(?!\S)|\s+
+// (ECMAScript, ordered alternation, "C" locale classes).  The scanner below implements that grammar directly.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+inline bool is_alpha(unsigned char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z'); }
+inline bool is_digit(unsigned char c) { return c >= '0' && c <= '9'; }
+inline bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+inline bool is_other(unsigned char c) { return !is_alpha(c) && !is_digit(c) && !is_space(c); }
+
+size_t match_len(const std::string& s, size_t p) {
+    static const char* const contractions[] = {"'s", "'t", "'re", "'ve", "'m", "'ll", "'d"};
+    const size_t n = s.size();
+    for (const char* c : contractions) {
+        const size_t l = strlen(c);
+        if (s.compare(p, l, c) == 0) return l;
+    }
+    bool (*const classes[3])(unsigned char) = {is_alpha, is_digit, is_other};
+    for (auto cls : classes) {
+        size_t q = p;
+        if (s[q] == ' ') q++;
+        if (q < n && cls((unsigned char)s[q])) {
+            while (q < n && cls((unsigned char)s[q])) q++;
+            return q - p;
+        }
+    }
+    if (is_space((unsigned char)s[p])) {
+        size_t e = p;
+        while (e < n && is_space((unsigned char)s[e])) e++;
+        if (e == n) return e - p;          // \s+(?!\S) at end of input
+        if (e - p >= 2) return e - p - 1;  // \s+(?!\S) backs off one character before a non-space
+        return e - p;                      // \s+
+    }
+    return 1;
+}
+}  // namespace
+
+std::vector<int32_t> tokenize(const Vocab& v, const char* text) {
+    const std::string str = text ? text : "";
+    std::vector<int32_t> out;
+    out.push_back(49406);   // <|startoftext|>, hard-coded in the reference (clip.cpp:637)
+    for (size_t p = 0; p < str.size();) {
+        const size_t l = match_len(str, p);
+        const std::string word = str.substr(p, l);
+        p += l;
+        const std::string whole = (word[0] == ' ' ? word.substr(1) : word) + "</w>";
+        auto it = v.token_to_id.find(whole);
+        if (it != v.token_to_id.end()) { out.push_back(it->second); continue; }
+        for (size_t i = 0; i < word.size();) {          // greedy longest match on the raw word (clip.cpp:655-668)
+            bool hit = false;
+            for (size_t j = word.size(); j > i; j--) {
+                auto c = v.token_to_id.find(word.substr(i, j - i));
+                if (c != v.token_to_id.end()) { out.push_back(c->second); i = j; hit = true; break; }
+            }
+            if (!hit) { fprintf(stderr, "clip_tokenize: unknown token '%c'\n", word[i]); i++; }
+        }
+    }
+    out.push_back(49407);   // <|endoftext|> (clip.cpp:671)
+    return out;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// preprocess: clip.cpp:728-927 -- PIL-style separable bicubic (Keys a = -0.5) with antialias support, clamp to
+// [0,255] after each pass, centre crop, (v/255 - mean)/std.  Arithmetic order is kept (double accumulation in
+// ascending tap order) so results are bit-identical to the reference (tests/test_host_ops.py).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+struct Taps {
+    int ksize = 0;
+    std::vector<double> k;     // [out][ksize]
+    std::vector<int> lo, cnt;  // first source index, number of taps
+};
+
+inline double keys_cubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+
+Taps make_taps(int in_size, int out_size) {
+    Taps t;
+    const float in0 = 0.0f, in1 = (float)in_size;
+    double support = 2.0, fs = (double)(in1 - in0) / out_size;
+    if (fs < 1.0) fs = 1.0;
+    support *= fs;
+    t.ksize = (int)ceil(support) * 2 + 1;
+    t.k.assign((size_t)out_size * t.ksize, 0.0);
+    t.lo.resize(out_size);
+    t.cnt.resize(out_size);
+    const double ss = 1.0 / fs;
+    for (int o = 0; o < out_size; o++) {
+        const double center = in0 + (o + 0.5) * (in1 - in0) / out_size;
+        int lo = (int)(center - support + 0.5);
+        if (lo < 0) lo = 0;
+        int hi = (int)(center + support + 0.5);
+        if (hi > in_size) hi = in_size;
+        const int cnt = hi - lo;
+        double* k = &t.k[(size_t)o * t.ksize];
+        double ww = 0.0;
+        for (int x = 0; x < cnt; x++) { const double w = keys_cubic((x + lo - center + 0.5) * ss); k[x] = w; ww += w; }
+        if (ww != 0.0) for (int x = 0; x < cnt; x++) k[x] /= ww;
+        t.lo[o] = lo;
+        t.cnt[o] = cnt;
+    }
+    return t;
+}
+inline float clamp255(double v) { return std::min(std::max((float)v, 0.0f), 255.0f); }
+}  // namespace
+
+bool preprocess_image(const uint8_t* src, int nx, int ny, int S, const float mean[3], const float stdv[3], float* dst) {
+    if (!src || nx <= 0 || ny <= 0 || S <= 0) return false;
+    const float scale = std::min((float)nx, (float)ny) / (float)S;
+    const int nx3 = (int)(nx / scale + 0.5f), ny3 = (int)(ny / scale + 0.5f);
+    if (nx3 < S || ny3 < S) return false;
+    const Taps th = make_taps(nx, nx3), tv = make_taps(ny, ny3);
+    std::vector<float> tmp((size_t)3 * nx3 * ny), res((size_t)3 * nx3 * ny3);
+    for (int y = 0; y < ny; y++)
+        for (int xx = 0; xx < nx3; xx++) {
+            const double* k = &th.k[(size_t)xx * th.ksize];
+            const int lo = th.lo[xx], cnt = th.cnt[xx];
+            for (int c = 0; c < 3; c++) {
+                double acc = 0.0;
+                for (int x = 0; x < cnt; x++) acc += (double)src[3 * ((size_t)y * nx + (x + lo)) + c] * k[x];
+                tmp[3 * ((size_t)y * nx3 + xx) + c] = clamp255(acc);
+            }
+        }
+    for (int yy = 0; yy < ny3; yy++) {
+        const double* k = &tv.k[(size_t)yy * tv.ksize];
+        const int lo = tv.lo[yy], cnt = tv.cnt[yy];
+        for (int x = 0; x < nx3; x++)
+            for (int c = 0; c < 3; c++) {
+                double acc = 0.0;
+                for (int y = 0; y < cnt; y++) acc += (double)tmp[3 * ((size_t)(y + lo) * nx3 + x) + c] * k[y];
+                res[3 * ((size_t)yy * nx3 + x) + c] = clamp255(acc);
+            }
+    }
+    const int xo = (nx3 - S) / 2, yo = (ny3 - S) / 2;
+    for (int y = 0; y < S; y++)
+        for (int x = 0; x < S; x++)
+            for (int c = 0; c < 3; c++) {
+                const float v = res[3 * ((size_t)(y + yo) * nx3 + (x + xo)) + c];
+                dst[3 * ((size_t)y * S + x) + c] = ((v / 255.0f) - mean[c]) / stdv[c];
+            }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// clip_model_quantize: clip.cpp:1661-1844.  Quantises every 2-D tensor whose name ends in "weight"
+// (regex ".*weight", clip.cpp:1711-1739) from f32/f16; everything else is copied.  The output container is
+// written exactly as the reference's gguf writer lays it out (ggml.c:20541-20640): version 2 header, source KVs
+// in order with general.file_type replaced and general.quantization_version = 2 appended, tensor infos with
+// recomputed offsets, 32-byte alignment padding.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+void put_str(std::string& b, const std::string& s) { const uint64_t n = s.size(); b.append((const char*)&n, 8); b.append(s); }
+template <class T> void put(std::string& b, T v) { b.append((const char*)&v, sizeof(T)); }
+bool ends_with_weight(const std::string& n) { return n.size() >= 6 && n.compare(n.size() - 6, 6, "weight") == 0; }
+}  // namespace
+
+bool quantize_file(const char* inp, const char* outp, int itype, std::string& err) {
+    if (!(itype == 2 || itype == 3 || itype == 6 || itype == 7 || itype == 8)) { err = "invalid quantization type"; return false; }
+    GgufFile g;
+    if (!g.parse(inp, err)) return false;
+    const size_t align = 32;
+    struct OutT { const GgufTensor* t; uint32_t type; std::vector<uint8_t> data; const uint8_t* ptr; size_t size; uint64_t offset; };
+    std::vector<OutT> outs(g.tensors.size());
+    uint64_t off = 0;
+    std::vector<float> f32buf;
+    for (size_t i = 0; i < g.tensors.size(); i++) {
+        const GgufTensor& t = g.tensors[i];
+        OutT& o = outs[i];
+        o.t = &t;
+        const bool q = ends_with_weight(t.name) && t.n_dims == 2;
+        if (q) {
+            if (t.type != 0 && t.type != 1) { err = "input must be f32 or f16"; return false; }
+            const int64_t k = (int64_t)t.ne[0], rows = (int64_t)t.ne[1];
+            if (k % 32) { err = "row length of " + t.name + " is not a multiple of 32"; return false; }
+            const size_t rb = (size_t)(k / 32) * ggml_type_block_bytes(itype);
+            o.data.resize((size_t)rows * rb);
+            f32buf.resize((size_t)k);
+            for (int64_t r = 0; r < rows; r++) {
+                dequant_row((int)t.type, t.data + (size_t)r * (t.type == 0 ? 4 : 2) * k, f32buf.data(), k);
+                quant_row(itype, f32buf.data(), o.data.data() + (size_t)r * rb, k);
+            }
+            o.type = (uint32_t)itype; o.ptr = o.data.data(); o.size = o.data.size();
+        } else {
+            o.type = t.type; o.ptr = t.data; o.size = t.nbytes;
+        }
+        o.offset = off;
+        off += (o.size + align - 1) / align * align;
+    }
+    std::string meta;
+    put<uint32_t>(meta, 0x46554747u);
+    put<uint32_t>(meta, 2u);                                   // GGUF_VERSION of the vendored ggml
+    put<uint64_t>(meta, (uint64_t)outs.size());
+    const bool has_qv = g.find("general.quantization_version") != nullptr;
+    put<uint64_t>(meta, (uint64_t)g.kvs.size() + (has_qv ? 0 : 1));
+    for (const GgufKV& kv : g.kvs) {
+        put_str(meta, kv.key);
+        if (kv.key == "general.file_type") { put<uint32_t>(meta, GT_U32); put<uint32_t>(meta, (uint32_t)itype); continue; }
+        if (kv.key == "general.quantization_version") { put<uint32_t>(meta, GT_U32); put<uint32_t>(meta, 2u); continue; }
+        put<uint32_t>(meta, kv.type);
+        meta.append((const char*)kv.raw, kv.raw_len);
+    }
+    if (!has_qv) { put_str(meta, "general.quantization_version"); put<uint32_t>(meta, GT_U32); put<uint32_t>(meta, 2u); }
+    for (const OutT& o : outs) {
+        put_str(meta, o.t->name);
+        put<uint32_t>(meta, o.t->n_dims);
+        for (uint32_t d = 0; d < o.t->n_dims; d++) put<uint64_t>(meta, o.t->ne[d]);
+        put<uint32_t>(meta, o.type);
+        put<uint64_t>(meta, o.offset);
+    }
+    meta.append((align - meta.size() % align) % align, '\0');
+    std::ofstream f(outp, std::ios::binary);
+    if (!f) { err = std::string("cannot open output ") + outp; return false; }
+    f.write(meta.data(), (std::streamsize)meta.size());
+    static const char zeros[32] = {0};
+    for (const OutT& o : outs) {
+        f.write((const char*)o.ptr, (std::streamsize)o.size);
+        f.write(zeros, (std::streamsize)((align - o.size % align) % align));
+    }
+    f.close();
+    if (!f) { err = "write failed"; return false; }
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// image files: binary PPM (P6, maxval 255) and 24-bit uncompressed BMP.  (The reference uses stb_image,
+// clip.cpp:709-726; JPEG/PNG decoding is host-side convenience outside the hot path and is not reproduced.)
+// ---------------------------------------------------------------------------------------------------
+bool load_image_file(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny) {
+    std::ifstream f(fname, std::ios::binary);
+    if (!f) return false;
+    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (buf.size() >= 2 && buf[0] == 'P' && buf[1] == '6') {
+        size_t p = 2;
+        int vals[3], got = 0;
+        while (got < 3 && p < buf.size()) {
+            while (p < buf.size() && is_space(buf[p])) p++;
+            if (p < buf.size() && buf[p] == '#') { while (p < buf.size() && buf[p] != '\n') p++; continue; }
+            int v = 0; bool any = false;
+            while (p < buf.size() && is_digit(buf[p])) { v = v * 10 + (buf[p] - '0'); p++; any = true; }
+            if (!any) return false;
+            vals[got++] = v;
+        }
+        if (got < 3 || vals[2] != 255) return false;
+        p++;   // single whitespace after maxval
+        nx = vals[0]; ny = vals[1];
+        const size_t need = (size_t)nx * ny * 3;
+        if (nx <= 0 || ny <= 0 || p + need > buf.size()) return false;
+        rgb.assign(buf.begin() + p, buf.begin() + p + need);
+        return true;
+    }
+    if (buf.size() >= 54 && buf[0] == 'B' && buf[1] == 'M') {
+        uint32_t offs; int32_t w, h; uint16_t bpp; uint32_t comp;
+        memcpy(&offs, &buf[10], 4); memcpy(&w, &buf[18], 4); memcpy(&h, &buf[22], 4); memcpy(&bpp, &buf[28], 2); memcpy(&comp, &buf[30], 4);
+        if (bpp != 24 || comp != 0 || w <= 0 || h == 0) return false;
+        const bool flip = h > 0;
+        const int hh = h > 0 ? h : -h;
+        const size_t stride = ((size_t)w * 3 + 3) & ~(size_t)3;
+        if (offs + stride * hh > buf.size()) return false;
+        nx = w; ny = hh;
+        rgb.resize((size_t)w * hh * 3);
+        for (int y = 0; y < hh; y++) {
+            const uint8_t* row = &buf[offs + stride * (flip ? (hh - 1 - y) : y)];
+            for (int x = 0; x < w; x++) { rgb[3 * ((size_t)y * w + x) + 0] = row[3 * x + 2]; rgb[3 * ((size_t)y * w + x) + 1] = row[3 * x + 1]; rgb[3 * ((size_t)y * w + x) + 2] = row[3 * x + 0]; }
+        }
+        return true;
+    }
+    return false;
+}
+
+}  // namespace cb

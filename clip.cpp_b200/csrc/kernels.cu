@@ -1,0 +1,269 @@
+// kernels.cu -- the memory-bound kernels around the GEMMs: LayerNorm (K2), im2col (K0a), embedding assembly (K4),
+// L2-normalise (K5), zero-shot scoring, plus a scalar debug GEMM.  All are HBM-bound streaming kernels: one warp per
+// row, 128-bit coalesced loads, warp-shuffle reductions, no shared memory.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace cb {
+
+namespace {
+
+CB_DEVINL float warp_sum(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+CB_DEVINL float warp_max(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+CB_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+CB_DEVINL float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// Two-pass LayerNorm statistics over a row produced by `load(i4)` (i4 = float4 index), as the reference does:
+// mean first, then the centred sum of squares (ggml.c:10822-10840).  The row is re-read (L1/L2 hits).
+template <class Load>
+CB_DEVINL void row_stats(Load load, int h4, int lane, float inv_h, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+    for (int i = lane; i < h4; i += 32) { const float4 v = load(i); s += (v.x + v.y) + (v.z + v.w); }
+    mean = warp_sum(s) * inv_h;
+    float q = 0.f;
+    for (int i = lane; i < h4; i += 32) {
+        const float4 v = load(i);
+        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+    rstd = rsqrtf(warp_sum(q) * inv_h + eps);
+}
+
+template <bool BF>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, size_t in_stride, int rows, int h, float eps,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        uint16_t* __restrict__ y) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * in_stride;
+    const int h4 = h >> 2;
+    auto load = [&](int i) { return ld4(xr + 4 * i); };
+    float mean, rstd;
+    row_stats(load, h4, lane, 1.0f / (float)h, eps, mean, rstd);
+    uint16_t* yr = y + (size_t)row * h;
+    for (int i = lane; i < h4; i += 32) {
+        const float4 v = load(i), g = ld4(gamma + 4 * i), b = ld4(beta + 4 * i);
+        const float o0 = (v.x - mean) * rstd * g.x + b.x, o1 = (v.y - mean) * rstd * g.y + b.y;
+        const float o2 = (v.z - mean) * rstd * g.z + b.z, o3 = (v.w - mean) * rstd * g.w + b.w;
+        uint2 pk;
+        pk.x = (uint32_t)P2<BF>::from_float(o0) | ((uint32_t)P2<BF>::from_float(o1) << 16);
+        pk.y = (uint32_t)P2<BF>::from_float(o2) | ((uint32_t)P2<BF>::from_float(o3) << 16);
+        *reinterpret_cast<uint2*>(yr + 4 * i) = pk;
+    }
+}
+
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ px, int B, int S, int P, int kpad,
+                                                     __half* __restrict__ out) {
+    const int np1 = S / P, K = 3 * P * P;
+    const size_t total = (size_t)B * np1 * np1 * kpad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(idx % kpad);
+        const size_t rowi = idx / kpad;
+        float v = 0.f;
+        if (k < K) {
+            const int p = (int)(rowi % (np1 * np1)), b = (int)(rowi / (np1 * np1));
+            const int py = p / np1, pxx = p % np1;
+            const int c = k / (P * P), rem = k % (P * P), ky = rem / P, kx = rem % P;
+            v = px[(((size_t)b * S + (py * P + ky)) * S + (pxx * P + kx)) * 3 + c];
+        }
+        out[idx] = __float2half_rn(v);
+    }
+}
+
+__global__ void __launch_bounds__(256) assemble_preln_kernel(const float* __restrict__ patch, const float* __restrict__ cls,
+                                                             const float* __restrict__ pos, int B, int T, int h, float eps,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             float* __restrict__ x) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= B * T) return;
+    const int b = row / T, t = row % T;
+    const float* src = (t == 0) ? cls : patch + ((size_t)b * (T - 1) + (t - 1)) * h;
+    const float* pr = pos + (size_t)t * h;
+    const int h4 = h >> 2;
+    auto load = [&](int i) { return add4(ld4(src + 4 * i), ld4(pr + 4 * i)); };
+    float mean, rstd;
+    row_stats(load, h4, lane, 1.0f / (float)h, eps, mean, rstd);
+    float* xr = x + (size_t)row * h;
+    for (int i = lane; i < h4; i += 32) {
+        const float4 v = load(i), g = ld4(gamma + 4 * i), bb = ld4(beta + 4 * i);
+        float4 o;
+        o.x = (v.x - mean) * rstd * g.x + bb.x; o.y = (v.y - mean) * rstd * g.y + bb.y;
+        o.z = (v.z - mean) * rstd * g.z + bb.z; o.w = (v.w - mean) * rstd * g.w + bb.w;
+        *reinterpret_cast<float4*>(xr + 4 * i) = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) text_embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tok,
+                                                         const float* __restrict__ pos, int nseq, int T, int h, int n_vocab,
+                                                         float* __restrict__ x) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= nseq * T) return;
+    int id = ids[row];
+    id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
+    const float* tr = tok + (size_t)id * h;
+    const float* pr = pos + (size_t)(row % T) * h;
+    float* xr = x + (size_t)row * h;
+    for (int i = lane; i < (h >> 2); i += 32) *reinterpret_cast<float4*>(xr + 4 * i) = add4(ld4(pr + 4 * i), ld4(tr + 4 * i));
+}
+
+__global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ v, float* __restrict__ out, int rows, int d,
+                                                     int normalize) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* vr = v + (size_t)row * d;
+    float s = 0.f;
+    for (int i = lane; i < d; i += 32) s += vr[i] * vr[i];
+    s = warp_sum(s);
+    const float inv = normalize ? 1.0f / sqrtf(s) : 1.0f;     // no epsilon, as the reference (clip.cpp:1164-1165)
+    for (int i = lane; i < d; i += 32) out[(size_t)row * d + i] = vr[i] * inv;
+}
+
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int h,
+                                                          int stride_rows, const int32_t* __restrict__ offs) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* s = src + ((size_t)row * stride_rows + (offs ? offs[row] : 0)) * h;
+    for (int i = lane; i < (h >> 2); i += 32) *reinterpret_cast<float4*>(dst + (size_t)row * h + 4 * i) = ld4(s + 4 * i);
+}
+
+// logits[i, j] = <img_i, txt_j>; small (n_img x n_txt x d), one warp per output element group
+__global__ void __launch_bounds__(256) logits_kernel(const float* __restrict__ img, const float* __restrict__ txt,
+                                                     float* __restrict__ out, int n_img, int n_txt, int d) {
+    const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= (size_t)n_img * n_txt) return;
+    const int i = (int)(w / n_txt), j = (int)(w % n_txt);
+    float s = 0.f;
+    for (int k = lane; k < d; k += 32) s += img[(size_t)i * d + k] * txt[(size_t)j * d + k];
+    s = warp_sum(s);
+    if (lane == 0) out[w] = s;
+}
+
+// p = (exp(s) + 1e-9) / sum  -- softmax_with_sorting's arithmetic without max subtraction (clip.cpp:1599-1607)
+__global__ void __launch_bounds__(256) softmax_plain_kernel(float* __restrict__ x, int rows, int cols) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float* r = x + (size_t)row * cols;
+    float s = 0.f;
+    for (int i = lane; i < cols; i += 32) { const float e = expf(r[i]) + 1e-9f; r[i] = e; s += e; }
+    s = warp_sum(s);
+    for (int i = lane; i < cols; i += 32) r[i] = r[i] / s;
+}
+
+// ---- debug scalar GEMM from raw ggml rows -----------------------------------------------------------
+CB_DEVINL float dq_elem(int qt, const uint8_t* row, int k) {
+    if (qt == QT_F16) return __half2float(reinterpret_cast<const __half*>(row)[k]);
+    const int bi = k >> 5, e = k & 31, j = e & 15, hi = e >> 4;
+    const int bs = qt == 2 ? 18 : qt == 3 ? 20 : qt == 6 ? 22 : qt == 7 ? 24 : 34;
+    const uint8_t* b = row + (size_t)bi * bs;
+    const float d = __half2float(*reinterpret_cast<const __half*>(b));
+    if (qt == 8) return (float)reinterpret_cast<const int8_t*>(b + 2)[e] * d;
+    float m = 0.f;
+    const uint8_t* qs;
+    uint32_t qh = 0;
+    if (qt == 2) qs = b + 2;
+    else if (qt == 3) { m = __half2float(*reinterpret_cast<const __half*>(b + 2)); qs = b + 4; }
+    else if (qt == 6) { qh = b[2] | (b[3] << 8) | (b[4] << 16) | ((uint32_t)b[5] << 24); qs = b + 6; }
+    else { m = __half2float(*reinterpret_cast<const __half*>(b + 2)); qh = b[4] | (b[5] << 8) | (b[6] << 16) | ((uint32_t)b[7] << 24); qs = b + 8; }
+    int q = hi ? (qs[j] >> 4) : (qs[j] & 0x0F);
+    if (qt == 6 || qt == 7) q |= ((qh >> (j + 16 * hi)) & 1) << 4;
+    if (qt == 2) q -= 8;
+    if (qt == 6) q -= 16;
+    return (float)q * d + m;
+}
+
+__global__ void naive_gemm_kernel(const uint16_t* __restrict__ x, int x_bf16, const uint8_t* __restrict__ w, int qt,
+                                  const float* __restrict__ bias, void* __restrict__ out, int M, int N, int K, int ldo, int epi,
+                                  int out_bf16, int scale_cols, float scale) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+    if (n >= N || m >= M) return;
+    const size_t rb = qt == QT_F16 ? (size_t)K * 2 : (size_t)(K / 32) * (qt == 2 ? 18 : qt == 3 ? 20 : qt == 6 ? 22 : qt == 7 ? 24 : 34);
+    const uint8_t* wr = w + (size_t)n * rb;
+    float acc = 0.f;
+    for (int k = 0; k < K; k++) {
+        const float xv = x_bf16 ? __bfloat162float(__ushort_as_bfloat16(x[(size_t)m * K + k])) : __half2float(__ushort_as_half(x[(size_t)m * K + k]));
+        float wv = dq_elem(qt, wr, k);
+        wv = x_bf16 ? __bfloat162float(__float2bfloat16_rn(wv)) : __half2float(__float2half_rn(wv));
+        acc += xv * wv;
+    }
+    float v = acc + (bias ? bias[n] : 0.f);
+    const size_t o = (size_t)m * ldo + n;
+    if (epi == EPI_RESID32) reinterpret_cast<float*>(out)[o] += v;
+    else if (epi == EPI_STORE32) reinterpret_cast<float*>(out)[o] = v;
+    else {
+        if (epi == EPI_GELU16) v = gelu_tanh(v);
+        else if (epi == EPI_QGELU16) v = gelu_quick(v);
+        else if (n < scale_cols) v *= scale;
+        reinterpret_cast<uint16_t*>(out)[o] = out_bf16 ? P2<true>::from_float(v) : P2<false>::from_float(v);
+    }
+}
+
+inline int rows_grid(int rows, int warps_per_block) { return (rows + warps_per_block - 1) / warps_per_block; }
+
+}  // namespace
+
+void launch_layernorm(const float* x, size_t in_stride, int rows, int h, float eps, const float* gamma, const float* beta,
+                      void* y16, int out_bf16, cudaStream_t st) {
+    if (rows <= 0) return;
+    if (out_bf16) layernorm_kernel<true><<<rows_grid(rows, 8), 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, (uint16_t*)y16);
+    else layernorm_kernel<false><<<rows_grid(rows, 8), 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, (uint16_t*)y16);
+}
+
+void launch_im2col(const float* pixels, int B, int S, int P, int kpad, void* patches16, cudaStream_t st) {
+    const size_t total = (size_t)B * (S / P) * (S / P) * kpad;
+    if (!total) return;
+    size_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    im2col_kernel<<<(int)blocks, 256, 0, st>>>(pixels, B, S, P, kpad, (__half*)patches16);
+}
+
+void launch_assemble_preln(const float* patch, const float* class_embd, const float* pos, int B, int T, int h, float eps,
+                           const float* gamma, const float* beta, float* x, cudaStream_t st) {
+    if (B * T <= 0) return;
+    assemble_preln_kernel<<<rows_grid(B * T, 8), 256, 0, st>>>(patch, class_embd, pos, B, T, h, eps, gamma, beta, x);
+}
+
+void launch_text_embed(const int32_t* ids, const float* tok, const float* pos, int nseq, int T, int h, int n_vocab, float* x,
+                       cudaStream_t st) {
+    if (nseq * T <= 0) return;
+    text_embed_kernel<<<rows_grid(nseq * T, 8), 256, 0, st>>>(ids, tok, pos, nseq, T, h, n_vocab, x);
+}
+
+void launch_l2norm(const float* v, float* out, int rows, int d, int normalize, cudaStream_t st) {
+    if (rows <= 0) return;
+    l2norm_kernel<<<rows_grid(rows, 8), 256, 0, st>>>(v, out, rows, d, normalize);
+}
+
+void launch_gather_rows(const float* src, float* dst, int rows, int h, int stride_rows, const int32_t* offs, cudaStream_t st) {
+    if (rows <= 0) return;
+    gather_rows_kernel<<<rows_grid(rows, 8), 256, 0, st>>>(src, dst, rows, h, stride_rows, offs);
+}
+
+void launch_logits(const float* img, const float* txt, float* logits, int n_img, int n_txt, int d, cudaStream_t st) {
+    const size_t n = (size_t)n_img * n_txt;
+    if (!n) return;
+    logits_kernel<<<(int)((n + 7) / 8), 256, 0, st>>>(img, txt, logits, n_img, n_txt, d);
+}
+
+void launch_softmax_plain(float* logits, int rows, int cols, cudaStream_t st) {
+    if (rows <= 0) return;
+    softmax_plain_kernel<<<rows_grid(rows, 8), 256, 0, st>>>(logits, rows, cols);
+}
+
+void launch_naive_gemm(const void* x16, int x_bf16, const void* w_ggml, int qtype, const float* bias, void* out, int M, int N,
+                       int K, int ldo, int epi, int out_bf16, int scale_cols, float scale, cudaStream_t st) {
+    if (M <= 0) return;
+    dim3 grid((N + 127) / 128, M);
+    naive_gemm_kernel<<<grid, 128, 0, st>>>((const uint16_t*)x16, x_bf16, (const uint8_t*)w_ggml, qtype, bias, out, M, N, K, ldo,
+                                            epi, out_bf16, scale_cols, scale);
+}
+
+}  // namespace cb

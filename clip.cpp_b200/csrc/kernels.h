@@ -1,0 +1,44 @@
+// kernels.h -- host launchers of the non-GEMM kernels (kernels.cu, attention.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cb {
+
+// K2 LayerNorm: y16[r, :] = ((x[r*in_stride ...] - mean) * rstd) * gamma + beta   (reference: ggml.c:10796-10845,
+// affine clip.cpp:1071-1074).  x fp32, row r starts at x + r*in_stride.  One warp per row.
+void launch_layernorm(const float* x, size_t in_stride, int rows, int h, float eps, const float* gamma, const float* beta,
+                      void* y16, int out_bf16, cudaStream_t st);
+
+// K0a im2col for the stride-P patch conv: pixels NHWC f32 [B,S,S,3] -> fp16 [B*Np, kpad], k = c*P*P + ky*P + kx,
+// zero padded to kpad (reference conv_2d im2col, ggml.c:13595-13631; pixel -> fp16 rounding ggml.c:13623).
+void launch_im2col(const float* pixels, int B, int S, int P, int kpad, void* patches16, cudaStream_t st);
+
+// K4v assemble + pre-LN: x[b,t,:] = LN( (t==0 ? class_embd : patch[b*Np+t-1,:]) + pos[t,:] ) * g + b  -> fp32
+// (clip.cpp:1315-1339)
+void launch_assemble_preln(const float* patch, const float* class_embd, const float* pos, int B, int T, int h, float eps,
+                           const float* gamma, const float* beta, float* x, cudaStream_t st);
+
+// K4t text embed: x[s*T+t,:] = tok[ids[s*T+t],:] + pos[t,:]   (clip.cpp:1059-1061), tables fp32 (dequantised at load)
+void launch_text_embed(const int32_t* ids, const float* tok, const float* pos, int nseq, int T, int h, int n_vocab, float* x,
+                       cudaStream_t st);
+
+// K3 attention: softmax(Q K^T [causal]) V per (sequence, head); qkv 16-bit [nseq*T, 3*H*64] (Q pre-scaled),
+// out 16-bit [nseq*T, H*64].  head_dim is fixed at 64.  (clip.cpp:1100-1108, 1382-1388)
+void launch_attention(const void* qkv16, void* out16, int nseq, int T, int H, int causal, int bf16, cudaStream_t st);
+
+// K5 head tail: out[r,:] = normalize ? v / sqrt(sum v^2) : v    (clip.cpp:1163-1166, 1448-1455)
+void launch_l2norm(const float* v, float* out, int rows, int d, int normalize, cudaStream_t st);
+
+// gather rows: dst[r,:] = src[idx(r),:] where idx(r) = r*stride_rows + offs[r] (offs may be null -> 0)
+void launch_gather_rows(const float* src, float* dst, int rows, int h, int stride_rows, const int32_t* offs, cudaStream_t st);
+
+// zero-shot scoring (clip.cpp:1591-1622 semantics per row): p = (exp(s) + 1e-9) / sum
+void launch_logits(const float* img, const float* txt, float* logits, int n_img, int n_txt, int d, cudaStream_t st);
+void launch_softmax_plain(float* logits, int rows, int cols, cudaStream_t st);
+
+// DEBUG ONLY (tests / CLIP_B200_DEBUG_NAIVE=1): scalar GEMM straight from ggml-format rows on the device.
+void launch_naive_gemm(const void* x16, int x_bf16, const void* w_ggml, int qtype, const float* bias, void* out, int M, int N,
+                       int K, int ldo, int epi, int out_bf16, int scale_cols, float scale, cudaStream_t st);
+
+}  // namespace cb

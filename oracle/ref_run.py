@@ -1,0 +1,73 @@
+"""oracle/ref_run.py -- TEST INFRASTRUCTURE.  Runs the UNMODIFIED reference (oracle/_ref/libclip_ref.so, built by
+oracle/Makefile from /root/reference) on given inputs, ONE MODEL PER PROCESS.
+
+Why a subprocess: the reference's batched-output node reads an uninitialised arena tensor
+(clip.cpp:1446-1454: `output` is created with ggml_new_tensor_2d and only ever ggml_acc'ed into), so results are
+only reproducible from a fresh process with single-image calls (fresh mmap'ed arena == zeros).  Mixing batch sizes
+or creating several contexts in one process yields garbage (verified, see DESIGN.md "oracle caveats").
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def available() -> bool:
+    return os.path.exists(os.path.join(HERE, "_ref", "libclip_ref.so"))
+
+
+def run_reference(model: str, images=None, token_seqs=None, n_threads: int = 0, normalize: bool = True, timing: bool = False):
+    """images: [n,S,S,3] f32 or None; token_seqs: list of int32 arrays or None.  Returns dict(img=, txt=[, img_s=, txt_s=])."""
+    with tempfile.TemporaryDirectory() as td:
+        inp, out = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
+        d = {"normalize": np.array(int(normalize)), "n_threads": np.array(n_threads)}
+        if images is not None:
+            d["images"] = np.ascontiguousarray(images, np.float32)
+        if token_seqs is not None:
+            d["tok_flat"] = np.concatenate([np.asarray(t, np.int32) for t in token_seqs]) if len(token_seqs) else np.zeros(0, np.int32)
+            d["tok_lens"] = np.array([len(t) for t in token_seqs], np.int64)
+        np.savez(inp, **d)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), model, inp, out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if r.returncode != 0:
+            raise RuntimeError("reference run failed:\n" + r.stderr.decode()[-2000:])
+        z = np.load(out)
+        return {k: z[k] for k in z.files}
+
+
+def _main():
+    import time
+    sys.path.insert(0, os.path.join(ROOT, "clip.cpp_b200"))
+    import binding as bd
+    model, inp, out = sys.argv[1:4]
+    z = np.load(inp)
+    nt = int(z["n_threads"]) or (os.cpu_count() or 4)
+    normalize = bool(int(z["normalize"]))
+    ref = bd.ClipLib(bd.REF_LIB)
+    ctx = ref.load(model, 0)
+    res = {}
+    if "images" in z.files:
+        imgs = z["images"]
+        t0 = time.perf_counter()
+        res["img"] = np.stack([ref.image_encode(ctx, np.ascontiguousarray(imgs[i]), normalize, nt) for i in range(len(imgs))]) \
+            if len(imgs) else np.zeros((0, 1), np.float32)
+        res["img_s"] = np.array(time.perf_counter() - t0)
+    if "tok_lens" in z.files:
+        lens, flat = z["tok_lens"], z["tok_flat"]
+        offs = np.concatenate([[0], np.cumsum(lens)])
+        t0 = time.perf_counter()
+        res["txt"] = np.stack([ref.text_encode(ctx, flat[offs[i]:offs[i + 1]], normalize, nt) for i in range(len(lens))]) \
+            if len(lens) else np.zeros((0, 1), np.float32)
+        res["txt_s"] = np.array(time.perf_counter() - t0)
+    res["threads"] = np.array(nt)
+    np.savez(out, **res)
+
+
+if __name__ == "__main__":
+    _main()
