@@ -68,6 +68,7 @@ EXTENSION_SYMBOLS = [
     "clip_b200_last_device_ms", "clip_b200_version", "clip_b200_set_micro_batch",
     "clip_b200_debug_gemm", "clip_b200_get_stream", "clip_b200_kernel_ms",
     "clip_b200_debug_repack_roundtrip", "clip_b200_debug_tokenize", "clip_b200_debug_preprocess",
+    "clip_b200_mark", "clip_b200_mark_elapsed_ms",
 ]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -155,6 +156,10 @@ class ClipLib:
             L.clip_b200_get_stream.argtypes = [vp]
             L.clip_b200_kernel_ms.restype = C.c_float
             L.clip_b200_kernel_ms.argtypes = [vp, ip, C.POINTER(C.c_uint64)]
+            L.clip_b200_mark.restype = C.c_bool
+            L.clip_b200_mark.argtypes = [vp, ip]
+            L.clip_b200_mark_elapsed_ms.restype = C.c_float
+            L.clip_b200_mark_elapsed_ms.argtypes = [vp, ip, ip]
             L.clip_b200_debug_repack_roundtrip.restype = C.c_int
             L.clip_b200_debug_repack_roundtrip.argtypes = [ip, vp, ip, ip]
             L.clip_b200_debug_tokenize.restype = C.c_int

@@ -798,6 +798,23 @@ void clip_b200_set_micro_batch(const struct clip_ctx* cc, int images, int sequen
     if (images > 0 && c->has_vision && c->vis.ws.cap_items == 0) c->vis.micro_batch = images;
     if (sequences > 0 && c->has_text && c->txt.ws.cap_items == 0) c->txt.micro_batch = sequences;
 }
+// CUDA-event stopwatch on the launch stream (slots 0..3) so that callers can time a region on the device
+static cudaEvent_t g_marks[4] = {nullptr, nullptr, nullptr, nullptr};
+bool clip_b200_mark(const struct clip_ctx* c, int slot) {
+    if (!c || slot < 0 || slot > 3) return false;
+    cudaSetDevice(c->device);
+    if (!g_marks[slot]) CK(cudaEventCreate(&g_marks[slot]));
+    CK(cudaEventRecord(g_marks[slot], c->stream));
+    return true;
+}
+float clip_b200_mark_elapsed_ms(const struct clip_ctx* c, int a, int b) {
+    if (!c || a < 0 || a > 3 || b < 0 || b > 3 || !g_marks[a] || !g_marks[b]) return -1.f;
+    cudaSetDevice(c->device);
+    if (cudaEventSynchronize(g_marks[b]) != cudaSuccess) return -1.f;
+    float ms = -1.f;
+    cudaEventElapsedTime(&ms, g_marks[a], g_marks[b]);
+    return ms;
+}
 uint64_t clip_b200_kernel_launches(const struct clip_ctx* c) { return c ? c->launches : 0; }
 float clip_b200_last_device_ms(const struct clip_ctx* c) { return c ? c->last_ms : 0.f; }
 float clip_b200_kernel_ms(const struct clip_ctx* cc, int kind, uint64_t* count) {

@@ -192,8 +192,10 @@ CB_DEVINL float gelu_tanh(float x) {   // reference formula: ggml/src/ggml.c:375
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
     return 0.5f * x * (1.0f + t);
 }
-CB_DEVINL float gelu_quick(float x) {  // x * sigmoid(1.702 x): ggml/src/ggml.c:3783-3785
-    return x * __frcp_rn(1.0f + __expf(-1.702f * x));
+CB_DEVINL float gelu_quick(float x) {  // x * sigmoid(1.702 x): ggml/src/ggml.c:3783-3785; sigmoid(z) = 0.5 + 0.5 tanh(z/2): one MUFU
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    return x * fmaf(0.5f, t, 0.5f);
 }
 
 }  // namespace cb

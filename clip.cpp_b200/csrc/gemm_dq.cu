@@ -63,9 +63,16 @@ struct KParams {
     float scale;
 };
 
-CB_DEVINL uint4 lds128(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
-CB_DEVINL void sts128(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    *reinterpret_cast<uint4*>(p) = make_uint4(a, b, c, d);
+// explicit .shared accesses on 32-bit shared-window addresses (generic ld/st would cost an address-space check)
+CB_DEVINL uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+CB_DEVINL uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+CB_DEVINL uint16_t lds16(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+CB_DEVINL void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 CB_DEVINL uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r;
@@ -78,13 +85,13 @@ CB_DEVINL uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // Arithmetic matches dequantize_row_q* (ggml/src/ggml.c:1496-1606): (q - zero) * d  or  q * d + m, with the
 // integer part exact (magic-number int->float) and ONE rounding of the product to the operand type.
 template <int QT, bool BF>
-CB_DEVINL void unpack_block(const uint8_t* __restrict__ q, uint8_t* __restrict__ w, int t) {
+CB_DEVINL void unpack_block(uint32_t q, uint32_t w, int t) {
     using P = P2<BF>;
     const int half = t >> 7, r = t & 127, sw = r & 7;
-    uint8_t* row = w + (r >> 3) * 1024 + sw * 128;
+    const uint32_t row = w + (r >> 3) * 1024 + sw * 128;
     if constexpr (QT == QT_Q8_0) {
         const uint4 qa = lds128(q + 16 * t), qb = lds128(q + 4096 + 16 * t);
-        const uint32_t d2 = P::splat_from_f16bits(*reinterpret_cast<const uint16_t*>(q + 8192 + 2 * t));
+        const uint32_t d2 = P::splat_from_f16bits(lds16(q + 8192 + 2 * t));
         const uint32_t words[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
         #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -111,14 +118,14 @@ CB_DEVINL void unpack_block(const uint8_t* __restrict__ q, uint8_t* __restrict__
         const uint4 qs = lds128(q + 16 * t);
         uint32_t hq = 0;
         uint32_t off = 4096;
-        if constexpr (Q5) { hq = *reinterpret_cast<const uint32_t*>(q + off + 4 * t); off += 1024; }
+        if constexpr (Q5) { hq = lds32(q + off + 4 * t); off += 1024; }
         uint32_t d2, m2 = 0;
         if constexpr (AFFINE) {
-            const uint32_t dm = *reinterpret_cast<const uint32_t*>(q + off + 4 * t);
+            const uint32_t dm = lds32(q + off + 4 * t);
             d2 = P::splat_from_f16bits((uint16_t)(dm & 0xffffu));
             m2 = P::splat_from_f16bits((uint16_t)(dm >> 16));
         } else {
-            d2 = P::splat_from_f16bits(*reinterpret_cast<const uint16_t*>(q + off + 2 * t));
+            d2 = P::splat_from_f16bits(lds16(q + off + 2 * t));
         }
         // zero point folded into the exact integer subtraction: 8 (q4_0), 16 (q5_0), 0 (q4_1 / q5_1)
         constexpr uint32_t ZP = (QT == QT_Q4_0) ? 8u : (QT == QT_Q5_0) ? 16u : 0u;
@@ -131,7 +138,6 @@ CB_DEVINL void unpack_block(const uint8_t* __restrict__ q, uint8_t* __restrict__
             for (int i = 0; i < 4; i++) {
                 uint32_t x = ((words[j] >> (4 * i)) & 0x000f000fu) | P::MAGIC;
                 if constexpr (Q5) {
-                    constexpr int dummy = 0; (void)dummy;
                     const int sh = 4 * j + i;   // 5th bits of this pair sit at bits sh and sh+16 -> move to bits 4 / 20
                     const uint32_t hb = (sh >= 4) ? (hq >> (sh - 4)) : (hq << (4 - sh));
                     x |= hb & 0x00100010u;
@@ -140,6 +146,49 @@ CB_DEVINL void unpack_block(const uint8_t* __restrict__ q, uint8_t* __restrict__
                 v[i] = AFFINE ? P::fma(qv, d2, m2) : P::mul(qv, d2);
             }
             sts128(row + (((4 * half + j) ^ sw) << 4), v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// Epilogue of one [128 features x 256 tokens] accumulator: this thread owns feature n (TMEM lane) and walks the token
+// columns 32 at a time.  For a fixed token the 32 lanes of a warp hold 32 consecutive features -> every global access
+// below is one fully coalesced 64-B (16-bit) or 128-B (fp32) request.  Specialised per epilogue kind at compile time.
+template <int EPI, bool BF>
+CB_DEVINL void epilogue_tile(const KParams& p, uint32_t acc_addr, int tok0, int n, float bias, float mul) {
+    const size_t ldo = (size_t)p.ldo;
+    #pragma unroll 1
+    for (int c = 0; c < BN / 32; c++) {
+        const int tbase = tok0 + c * 32;
+        if (tbase >= p.M) break;                  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32(acc_addr + c * 32, r);
+        const int nvalid = min(32, p.M - tbase);
+        if constexpr (EPI == EPI_RESID32) {
+            float* o = reinterpret_cast<float*>(p.out) + (size_t)tbase * ldo + n;
+            float old[32];
+            #pragma unroll
+            for (int j = 0; j < 32; j++) old[j] = (j < nvalid) ? o[(size_t)j * ldo] : 0.f;   // 32 independent loads in flight
+            tmem_ld_wait();
+            #pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (j < nvalid) o[(size_t)j * ldo] = old[j] + (__uint_as_float(r[j]) + bias);
+        } else if constexpr (EPI == EPI_STORE32) {
+            tmem_ld_wait();
+            float* o = reinterpret_cast<float*>(p.out) + (size_t)tbase * ldo + n;
+            #pragma unroll
+            for (int j = 0; j < 32; j++)
+                if (j < nvalid) o[(size_t)j * ldo] = __uint_as_float(r[j]) + bias;
+        } else {
+            tmem_ld_wait();
+            uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + (size_t)tbase * ldo + n;
+            #pragma unroll
+            for (int j = 0; j < 32; j++) {
+                float v = __uint_as_float(r[j]) + bias;
+                if constexpr (EPI == EPI_GELU16) v = gelu_tanh(v);
+                else if constexpr (EPI == EPI_QGELU16) v = gelu_quick(v);
+                else v *= mul;
+                if (j < nvalid) o[(size_t)j * ldo] = P2<BF>::from_float(v);
+            }
         }
     }
 }
@@ -254,36 +303,13 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             mbar_wait(acc_full + 8 * as, aph);
             tc_fence_after();
             const int tok0 = tt * BN;
-            #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                if (tok0 + c * 32 >= p.M) break;                  // warp-uniform
-                uint32_t r[32];
-                tmem_ld_32x32(lane_addr + as * BN + c * 32, r);
-                tmem_ld_wait();
-                const int tbase = tok0 + c * 32;
-                const int nvalid = min(32, p.M - tbase);
-                if (p.epi == EPI_RESID32) {
-                    float* o = reinterpret_cast<float*>(p.out) + (size_t)tbase * p.ldo + n;
-                    #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (j < nvalid) o[(size_t)j * p.ldo] += __uint_as_float(r[j]) + bias;
-                } else if (p.epi == EPI_STORE32) {
-                    float* o = reinterpret_cast<float*>(p.out) + (size_t)tbase * p.ldo + n;
-                    #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if (j < nvalid) o[(size_t)j * p.ldo] = __uint_as_float(r[j]) + bias;
-                } else {
-                    uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + (size_t)tbase * p.ldo + n;
-                    #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        float v = __uint_as_float(r[j]) + bias;
-                        if (p.epi == EPI_GELU16) v = gelu_tanh(v);
-                        else if (p.epi == EPI_QGELU16) v = gelu_quick(v);
-                        else v *= mul;
-                        const uint16_t h = p.out_bf16 ? P2<true>::from_float(v) : P2<false>::from_float(v);
-                        if (j < nvalid) o[(size_t)j * p.ldo] = h;
-                    }
-                }
+            const uint32_t acc_addr = lane_addr + as * BN;
+            switch (p.epi) {
+            case EPI_STORE16: epilogue_tile<EPI_STORE16, BF>(p, acc_addr, tok0, n, bias, mul); break;
+            case EPI_GELU16: epilogue_tile<EPI_GELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
+            case EPI_QGELU16: epilogue_tile<EPI_QGELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
+            case EPI_RESID32: epilogue_tile<EPI_RESID32, BF>(p, acc_addr, tok0, n, bias, mul); break;
+            default: epilogue_tile<EPI_STORE32, BF>(p, acc_addr, tok0, n, bias, mul); break;
             }
             tc_fence_before();
             __syncwarp();
@@ -297,7 +323,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             for (int kb = 0; kb < nkb; kb++) {
                 mbar_wait(in_full + 8 * s, ph);
                 mbar_wait(w_empty + 8 * ws, wph ^ 1);
-                unpack_block<DQ ? QT : QT_Q4_0, BF>(smem + s * IN_STAGE + X_STAGE, smem + W_RING + ws * W_STAGE, t);
+                unpack_block<DQ ? QT : QT_Q4_0, BF>(smem_base + s * IN_STAGE + X_STAGE, smem_base + W_RING + ws * W_STAGE, t);
                 fence_proxy_async_smem();      // st.shared (generic proxy) -> visible to UMMA (async proxy)
                 __syncwarp();
                 if (lane == 0) {

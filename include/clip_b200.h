@@ -192,6 +192,9 @@ float    clip_b200_last_device_ms(const struct clip_ctx * ctx);    /* CUDA-event
 /* per-kernel-class CUDA-event time accumulated since the last call with the same kind (0 GEMM, 1 attention,
  * 2 layernorm, 3 other); *count receives the number of launches.  Enabled by env CLIP_B200_PROFILE=1. */
 float    clip_b200_kernel_ms(const struct clip_ctx * ctx, int kind, uint64_t * count);
+/* CUDA-event stopwatch on the launch stream: mark(slot 0..3), then elapsed(a, b) in ms (-1 on error) */
+bool     clip_b200_mark(const struct clip_ctx * ctx, int slot);
+float    clip_b200_mark_elapsed_ms(const struct clip_ctx * ctx, int a, int b);
 const char * clip_b200_last_error(void);
 const char * clip_b200_version(void);
 

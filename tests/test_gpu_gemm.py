@@ -23,19 +23,64 @@ def round16(a, bf16):
     return u.astype(np.uint32).view(np.float32)
 
 
+def decode_blocks(qt, raw, N, K):
+    """Independent numpy decoder of the ggml block formats (ggml.c:866-911): returns integer quants q [N,K] (with the
+    zero point already subtracted for q4_0/q5_0), per-element d and m (fp32 values of the stored fp16 scale / min)."""
+    bs = {"q4_0": 18, "q4_1": 20, "q5_0": 22, "q5_1": 24, "q8_0": 34}[qt]
+    b = np.frombuffer(raw, np.uint8).reshape(N, K // 32, bs)
+    d = b[:, :, 0:2].copy().view(np.float16)[..., 0].astype(np.float32)
+    m = np.zeros_like(d)
+    o = 2
+    if qt in ("q4_1", "q5_1"):
+        m = b[:, :, 2:4].copy().view(np.float16)[..., 0].astype(np.float32)
+        o = 4
+    if qt == "q8_0":
+        q = b[:, :, 2:34].copy().view(np.int8).astype(np.int32)
+    else:
+        qh = np.zeros(d.shape, np.uint32)
+        if qt in ("q5_0", "q5_1"):
+            qh = b[:, :, o:o + 4].copy().view(np.uint32)[..., 0]
+            o += 4
+        qs = b[:, :, o:o + 16].astype(np.int32)
+        lo, hi = qs & 15, qs >> 4
+        j = np.arange(16)
+        if qt in ("q5_0", "q5_1"):
+            lo = lo | (((qh[..., None] >> j) & 1).astype(np.int32) << 4)
+            hi = hi | (((qh[..., None] >> (j + 16)) & 1).astype(np.int32) << 4)
+        q = np.concatenate([lo, hi], axis=-1)
+        if qt == "q4_0":
+            q = q - 8
+        if qt == "q5_0":
+            q = q - 16
+    rep = lambda a: np.repeat(a, 32, axis=1)
+    return q.reshape(N, K), rep(d), rep(m)
+
+
 def make_weight(qt, N, K, rng):
+    """returns (raw ggml bytes, decoded (q, d, m) or the fp16 matrix)."""
     w = (rng.standard_normal((N, K)) * 0.05).astype(np.float32)
     if qt == "f16":
-        raw = w.astype(np.float16).tobytes()
-        deq = w.astype(np.float16).astype(np.float32)
-    else:
-        raw = orc.quantize_rows(QT[qt], w)
-        deq = np.empty((N, K), np.float32)
-        buf = np.frombuffer(raw, np.uint8)
-        rs = len(raw) // N
-        for r in range(N):
-            orc.lib().orc_dequantize_row(QT[qt], buf.ctypes.data + r * rs, deq[r].ctypes.data_as(C.POINTER(C.c_float)), K)
-    return raw, deq
+        return w.astype(np.float16).tobytes(), w.astype(np.float16).astype(np.float32)
+    raw = orc.quantize_rows(QT[qt], w)
+    q, d, m = decode_blocks(qt, raw, N, K)
+    # cross-check the numpy decoder against the oracle's dequantizer (bit-exact)
+    deq = np.empty((N, K), np.float32)
+    buf = np.frombuffer(raw, np.uint8)
+    rs = len(raw) // N
+    for r in range(0, N, 17):
+        orc.lib().orc_dequantize_row(QT[qt], buf.ctypes.data + r * rs, deq[r].ctypes.data_as(C.POINTER(C.c_float)), K)
+        assert np.array_equal(deq[r], (q[r].astype(np.float32) * d[r] + m[r]).astype(np.float32))
+    return raw, (q, d, m)
+
+
+def unpacked(wdesc, bf16):
+    """The operand-type weight exactly as the unpack warps build it: scale (and min) converted to the operand type,
+    integer part exact, ONE rounding of q*d (+m) to the operand type."""
+    if not isinstance(wdesc, tuple):
+        return wdesc
+    q, d, m = wdesc
+    d16, m16 = round16(d, bf16).astype(np.float64), round16(m, bf16).astype(np.float64)
+    return round16((q.astype(np.float64) * d16 + m16).astype(np.float32), bf16)
 
 
 def run_gemm(prod, qt, bf16, M, N, K, epi, x, raw, bias, resid=None, naive=0):
@@ -51,7 +96,7 @@ def run_gemm(prod, qt, bf16, M, N, K, epi, x, raw, bias, resid=None, naive=0):
 
 
 def expected(x, deq, bias, bf16, epi, resid, N):
-    xr, wr = round16(x, bf16).astype(np.float64), round16(deq, bf16).astype(np.float64)
+    xr, wr = round16(x, bf16).astype(np.float64), unpacked(deq, bf16).astype(np.float64)
     acc = (xr @ wr.T).astype(np.float32)
     v = acc + (bias if bias is not None else 0)
     if epi == EPI_STORE32:
@@ -116,8 +161,9 @@ def test_gemm_matches_scalar_debug_kernel(prod):
     M, N, K = 513, 256, 1024
     raw, _ = make_weight("q5_1", N, K, rng)
     x = rng.standard_normal((M, K)).astype(np.float32)
-    a, _ = run_gemm(prod, "q5_1", True, M, N, K, EPI_STORE32, x, raw, None)
-    b, _ = run_gemm(prod, "q5_1", True, M, N, K, EPI_STORE32, x, raw, None, naive=1)
+    # fp16 operands: d and m are exact in both kernels, so the two differ only by fp32 summation order
+    a, _ = run_gemm(prod, "q5_1", False, M, N, K, EPI_STORE32, x, raw, None)
+    b, _ = run_gemm(prod, "q5_1", False, M, N, K, EPI_STORE32, x, raw, None, naive=1)
     assert np.abs(a - b).max() <= 1e-3 * max(1.0, np.abs(b).max())
 
 
