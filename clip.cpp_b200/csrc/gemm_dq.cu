@@ -13,12 +13,14 @@
 //     (32 lanes = 32 consecutive features of one token), no shared-memory transpose needed.
 //
 // Warp roles (persistent CTA, 1 per SM, 512 threads; 256 for unquantized f16 weights):
-//   warp 0      TMA producer: activation box [256 x 64] (UTMALDG, 128B swizzle) + ONE bulk copy (UBLKCP) of the
-//               packed 32-weight blocks + scales of the [128 x 64] weight tile (wpack.h)       -> in_full[s]
-//   warps 8-15  unpack: packed q4_0/q4_1/q5_0/q5_1/q8_0 blocks -> fp16/bf16 A tile in the UMMA
-//               K-major/128B-swizzle layout (st.shared.v4, conflict-free)                        -> w_full[j]
+//   warp 0      X producer: activation box [256 tokens x 64 k] (UTMALDG, 128B swizzle)            -> x_full[s]
+//   warp 3      Q producer: ONE 1-D bulk copy (UBLKCP) per k-block of the packed 32-weight blocks + scales of
+//               the [128 x 64] weight tile (wpack.h); runs up to 8 k-blocks ahead                  -> q_full[s]
+//   warps 8-15  unpack, 4 groups x 2 warps; group g owns k-blocks i = g (mod 4), so four k-blocks are being
+//               unpacked concurrently (hides mbarrier / proxy-fence latency): packed q4_0/q4_1/q5_0/q5_1/q8_0
+//               -> fp16/bf16 A tile in the UMMA K-major/128B-swizzle layout (st.shared.v4)        -> w_full[j]
 //   warp 1      one thread issues tcgen05.mma (M128 N256 K16, kind::f16), fp32 accumulators in TMEM,
-//               tcgen05.commit releases input stages / signals the epilogue
+//               tcgen05.commit releases the X / W stages and signals the epilogue
 //   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / scale / GELU / residual -> coalesced global stores;
 //               double-buffered accumulators (2 x 256 TMEM columns) overlap it with the next tile's MMAs
 //   warp 2      TMEM alloc / dealloc
@@ -37,20 +39,29 @@ namespace {
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
 constexpr int X_STAGE = BN * BK * 2;   // 32768 B
 constexpr int W_STAGE = BM * BK * 2;   // 16384 B
-constexpr int SI = 4;                  // input ring depth (activation box + packed weights)
-constexpr int SW = 3;                  // unpacked-weight ring depth
-constexpr int N_UNPACK_WARPS = 8;
+constexpr int N_GROUPS = 4;            // unpack groups (2 warps each)
 constexpr int N_EPI_WARPS = 4;
 constexpr uint32_t TMEM_COLS = 512;    // 2 accumulator stages x 256 columns
 
 __host__ __device__ constexpr uint32_t chunk_bytes(int qt) {
     return qt == 2 ? 4608u : qt == 3 ? 5120u : qt == 6 ? 5632u : qt == 7 ? 6144u : qt == 8 ? 8704u : 0u;
 }
-__host__ __device__ constexpr uint32_t chunk_pad(int qt) { return (chunk_bytes(qt) + 1023u) & ~1023u; }
-__host__ __device__ constexpr uint32_t in_stage_bytes(int qt) { return X_STAGE + (qt == 1 ? (uint32_t)W_STAGE : chunk_pad(qt)); }
-__host__ __device__ constexpr uint32_t smem_bytes(int qt) {
-    return SI * in_stage_bytes(qt) + (qt == 1 ? 0u : (uint32_t)(SW * W_STAGE)) + 256u /*barriers*/ + 1024u /*align slack*/;
-}
+// shared-memory plan per weight type (all rings fit the 227 KB carve-out)
+template <int QT>
+struct Cfg {
+    static constexpr bool DQ = (QT != QT_F16);
+    static constexpr uint32_t CHUNK = chunk_bytes(QT);
+    static constexpr int SX = DQ ? 3 : 4;                              // X ring (f16: X + W per stage)
+    static constexpr int SW = DQ ? (QT == QT_Q8_0 ? 4 : 5) : 0;        // unpacked-weight ring
+    static constexpr int SQ = DQ ? (QT == QT_Q8_0 ? 6 : 8) : 0;        // packed-weight ring
+    static constexpr uint32_t XS = DQ ? (uint32_t)X_STAGE : (uint32_t)(X_STAGE + W_STAGE);
+    static constexpr uint32_t W_OFF = SX * XS;
+    static constexpr uint32_t Q_OFF = W_OFF + SW * W_STAGE;
+    static constexpr uint32_t BAR_OFF = Q_OFF + SQ * CHUNK;
+    static constexpr uint32_t SMEM = BAR_OFF + 512 /*barriers*/ + 1024 /*align slack*/;
+    static_assert(SMEM <= 232448, "shared memory plan exceeds 227 KB");
+    static_assert(!DQ || (SW >= N_GROUPS && SQ >= N_GROUPS), "rings must cover the concurrent unpack groups");
+};
 
 struct KParams {
     CUtensorMap tm_x;
@@ -59,7 +70,7 @@ struct KParams {
     const float* bias;
     void* out;
     int M, N, K, ldo;
-    int epi, out_bf16, scale_cols;
+    int epi, scale_cols;
     float scale;
 };
 
@@ -152,80 +163,84 @@ CB_DEVINL void unpack_block(uint32_t q, uint32_t w, int t) {
 
 // Epilogue of one [128 features x 256 tokens] accumulator: this thread owns feature n (TMEM lane) and walks the token
 // columns 32 at a time.  For a fixed token the 32 lanes of a warp hold 32 consecutive features -> every global access
-// below is one fully coalesced 64-B (16-bit) or 128-B (fp32) request.  Specialised per epilogue kind at compile time.
+// below is one fully coalesced 64-B (16-bit) or 128-B (fp32) request.  Specialised per epilogue kind at compile time;
+// element offsets are 32-bit (host checks M*ldo < 2^32) so each access costs one IADD + one IMAD.WIDE.
+template <int EPI, bool BF, bool FULL>
+CB_DEVINL void epilogue_chunk(const KParams& p, const uint32_t (&r)[32], uint32_t off, uint32_t ldo, int nvalid, float bias, float mul) {
+    if constexpr (EPI == EPI_RESID32) {
+        float* base = reinterpret_cast<float*>(p.out);
+        #pragma unroll
+        for (int h = 0; h < 2; h++) {              // two batches of 16 independent loads (register budget: 128/thread)
+            float old[16];
+            uint32_t o = off + (uint32_t)(16 * h) * ldo;
+            #pragma unroll
+            for (int j = 0; j < 16; j++, o += ldo) old[j] = (FULL || 16 * h + j < nvalid) ? base[o] : 0.f;
+            o = off + (uint32_t)(16 * h) * ldo;
+            #pragma unroll
+            for (int j = 0; j < 16; j++, o += ldo)
+                if (FULL || 16 * h + j < nvalid) base[o] = old[j] + (__uint_as_float(r[16 * h + j]) + bias);
+        }
+    } else if constexpr (EPI == EPI_STORE32) {
+        float* base = reinterpret_cast<float*>(p.out);
+        uint32_t o = off;
+        #pragma unroll
+        for (int j = 0; j < 32; j++, o += ldo)
+            if (FULL || j < nvalid) base[o] = __uint_as_float(r[j]) + bias;
+    } else {
+        uint16_t* base = reinterpret_cast<uint16_t*>(p.out);
+        uint32_t o = off;
+        #pragma unroll
+        for (int j = 0; j < 32; j++, o += ldo) {
+            float v = __uint_as_float(r[j]) + bias;
+            if constexpr (EPI == EPI_GELU16) v = gelu_tanh(v);
+            else if constexpr (EPI == EPI_QGELU16) v = gelu_quick(v);
+            else v *= mul;
+            if (FULL || j < nvalid) base[o] = P2<BF>::from_float(v);
+        }
+    }
+}
+
 template <int EPI, bool BF>
 CB_DEVINL void epilogue_tile(const KParams& p, uint32_t acc_addr, int tok0, int n, float bias, float mul) {
-    const size_t ldo = (size_t)p.ldo;
+    const uint32_t ldo = (uint32_t)p.ldo;
+    const int ntok = min(BN, p.M - tok0);
+    uint32_t off = (uint32_t)tok0 * ldo + (uint32_t)n;
     #pragma unroll 1
-    for (int c = 0; c < BN / 32; c++) {
-        const int tbase = tok0 + c * 32;
-        if (tbase >= p.M) break;                  // warp-uniform
+    for (int c = 0; c < BN / 32; c++, off += 32u * ldo) {
+        const int nvalid = ntok - c * 32;
+        if (nvalid <= 0) break;                    // warp-uniform
         uint32_t r[32];
         tmem_ld_32x32(acc_addr + c * 32, r);
-        const int nvalid = min(32, p.M - tbase);
-        if constexpr (EPI == EPI_RESID32) {
-            float* o = reinterpret_cast<float*>(p.out) + (size_t)tbase * ldo + n;
-            float old[32];
-            #pragma unroll
-            for (int j = 0; j < 32; j++) old[j] = (j < nvalid) ? o[(size_t)j * ldo] : 0.f;   // 32 independent loads in flight
-            tmem_ld_wait();
-            #pragma unroll
-            for (int j = 0; j < 32; j++)
-                if (j < nvalid) o[(size_t)j * ldo] = old[j] + (__uint_as_float(r[j]) + bias);
-        } else if constexpr (EPI == EPI_STORE32) {
-            tmem_ld_wait();
-            float* o = reinterpret_cast<float*>(p.out) + (size_t)tbase * ldo + n;
-            #pragma unroll
-            for (int j = 0; j < 32; j++)
-                if (j < nvalid) o[(size_t)j * ldo] = __uint_as_float(r[j]) + bias;
-        } else {
-            tmem_ld_wait();
-            uint16_t* o = reinterpret_cast<uint16_t*>(p.out) + (size_t)tbase * ldo + n;
-            #pragma unroll
-            for (int j = 0; j < 32; j++) {
-                float v = __uint_as_float(r[j]) + bias;
-                if constexpr (EPI == EPI_GELU16) v = gelu_tanh(v);
-                else if constexpr (EPI == EPI_QGELU16) v = gelu_quick(v);
-                else v *= mul;
-                if (j < nvalid) o[(size_t)j * ldo] = P2<BF>::from_float(v);
-            }
-        }
+        tmem_ld_wait();
+        if (nvalid >= 32) epilogue_chunk<EPI, BF, true>(p, r, off, ldo, 32, bias, mul);
+        else epilogue_chunk<EPI, BF, false>(p, r, off, ldo, nvalid, bias, mul);
     }
 }
 
 template <int QT, bool BF>
 __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(const __grid_constant__ KParams p) {
-    constexpr bool DQ = (QT != QT_F16);
-    constexpr uint32_t CHUNK = chunk_bytes(QT);
-    constexpr uint32_t IN_STAGE = in_stage_bytes(QT);
-    constexpr uint32_t W_RING = SI * IN_STAGE;                         // only for DQ
-    constexpr uint32_t BAR_OFF = SI * IN_STAGE + (DQ ? SW * W_STAGE : 0);
+    using C = Cfg<QT>;
+    constexpr bool DQ = C::DQ;
+    constexpr int SX = C::SX, SW = DQ ? C::SW : 1, SQ = DQ ? C::SQ : 1;
     constexpr uint32_t IDESC = umma_idesc(BF, BM, BN);
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bars = smem_base + BAR_OFF;
+    const uint32_t bars = smem_base + C::BAR_OFF;
     // barrier slots (8 B each)
-    const uint32_t in_full = bars, in_empty = bars + 8 * SI, w_full = bars + 16 * SI, w_empty = w_full + 8 * SW,
-                   acc_full = w_empty + 8 * SW, acc_empty = acc_full + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * SI + 16 * SW + 32);
+    const uint32_t x_full = bars, x_empty = x_full + 8 * SX, q_full = x_empty + 8 * SX, q_empty = q_full + 8 * SQ,
+                   w_full = q_empty + 8 * SQ, w_empty = w_full + 8 * SW, acc_full = w_empty + 8 * SW, acc_empty = acc_full + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 16 * SX + 16 * SQ + 16 * SW + 32);
+    static_assert(16 * C::SX + 16 * (DQ ? C::SQ : 1) + 16 * (DQ ? C::SW : 1) + 32 + 4 <= 512, "barrier area");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SI; i++) {
-            mbar_init(in_full + 8 * i, 1);
-            mbar_init(in_empty + 8 * i, DQ ? 1 + N_UNPACK_WARPS : 1);
-        }
-        for (int i = 0; i < SW; i++) {
-            mbar_init(w_full + 8 * i, N_UNPACK_WARPS);
-            mbar_init(w_empty + 8 * i, 1);
-        }
-        for (int i = 0; i < 2; i++) {
-            mbar_init(acc_full + 8 * i, 1);
-            mbar_init(acc_empty + 8 * i, N_EPI_WARPS);
-        }
+        for (int i = 0; i < SX; i++) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); }
+        for (int i = 0; i < SQ; i++) { mbar_init(q_full + 8 * i, 1); mbar_init(q_empty + 8 * i, 2); }
+        for (int i = 0; i < SW; i++) { mbar_init(w_full + 8 * i, 2); mbar_init(w_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, N_EPI_WARPS); }
         mbar_fence_init();
         tma_prefetch_desc(&p.tm_x);
         if (!DQ) tma_prefetch_desc(&p.tm_w);
@@ -237,28 +252,42 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
     const uint32_t tmem_base = *tmem_slot;
 
     const int n_ft = p.N / BM, n_tt = (p.M + BN - 1) / BN, n_tiles = n_ft * n_tt, nkb = p.K / BK;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    const int total_kb = my_tiles * nkb;                                                      // k-blocks of this CTA
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ TMA producer
+        // ------------------------------------------------------------------ X producer (f16: X and W)
         uint32_t s = 0, ph = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int ft = tile % n_ft, tt = tile / n_ft;
             for (int kb = 0; kb < nkb; kb++) {
-                mbar_wait(in_empty + 8 * s, ph ^ 1);
+                mbar_wait(x_empty + 8 * s, ph ^ 1);
                 if (lane == 0) {
-                    const uint32_t dst = smem_base + s * IN_STAGE;
-                    if constexpr (DQ) {
-                        mbar_arrive_expect_tx(in_full + 8 * s, X_STAGE + CHUNK);
-                        tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, in_full + 8 * s);
-                        bulk_load_1d(dst + X_STAGE, p.w_packed + ((size_t)ft * nkb + kb) * CHUNK, CHUNK, in_full + 8 * s);
-                    } else {
-                        mbar_arrive_expect_tx(in_full + 8 * s, X_STAGE + W_STAGE);
-                        tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, in_full + 8 * s);
-                        tma_load_2d(dst + X_STAGE, &p.tm_w, kb * BK, ft * BM, in_full + 8 * s);
-                    }
+                    const uint32_t dst = smem_base + s * C::XS;
+                    mbar_arrive_expect_tx(x_full + 8 * s, C::XS);
+                    tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, x_full + 8 * s);
+                    if constexpr (!DQ) tma_load_2d(dst + X_STAGE, &p.tm_w, kb * BK, ft * BM, x_full + 8 * s);
                 }
                 __syncwarp();
-                if (++s == SI) { s = 0; ph ^= 1; }
+                if (++s == SX) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ Q producer (packed weight blocks)
+        if constexpr (DQ) {
+            uint32_t s = 0, ph = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int ft = tile % n_ft;
+                const uint8_t* src = p.w_packed + (size_t)ft * nkb * C::CHUNK;
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(q_empty + 8 * s, ph ^ 1);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(q_full + 8 * s, C::CHUNK);
+                        bulk_load_1d(smem_base + C::Q_OFF + s * C::CHUNK, src + (size_t)kb * C::CHUNK, C::CHUNK, q_full + 8 * s);
+                    }
+                    __syncwarp();
+                    if (++s == SQ) { s = 0; ph ^= 1; }
+                }
             }
         }
     } else if (warp == 1) {
@@ -270,22 +299,22 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             mbar_wait(acc_empty + 8 * as, aph ^ 1);
             tc_fence_after();
             for (int kb = 0; kb < nkb; kb++) {
-                mbar_wait(in_full + 8 * s, ph);
+                mbar_wait(x_full + 8 * s, ph);
                 if constexpr (DQ) mbar_wait(w_full + 8 * ws, wph);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t xa = smem_base + s * IN_STAGE;
-                    const uint32_t wa = DQ ? (smem_base + W_RING + ws * W_STAGE) : (xa + X_STAGE);
+                    const uint32_t xa = smem_base + s * C::XS;
+                    const uint32_t wa = DQ ? (smem_base + C::W_OFF + ws * W_STAGE) : (xa + X_STAGE);
                     const uint64_t da = umma_desc_k128(wa), db = umma_desc_k128(xa);
                     #pragma unroll
                     for (int k = 0; k < BK / 16; k++)   // advance 16 elements = 32 B = 2 descriptor units
                         umma_f16(tmem_base + as * BN, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(in_empty + 8 * s);
+                    umma_commit(x_empty + 8 * s);
                     if constexpr (DQ) umma_commit(w_empty + 8 * ws);
                     if (kb == nkb - 1) umma_commit(acc_full + 8 * as);
                 }
                 __syncwarp();
-                if (++s == SI) { s = 0; ph ^= 1; }
+                if (++s == SX) { s = 0; ph ^= 1; }
                 if constexpr (DQ) { if (++ws == SW) { ws = 0; wph ^= 1; } }
             }
         }
@@ -315,23 +344,27 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * as);
         }
-    } else if (DQ && warp >= 8) {
-        // ------------------------------------------------------------------ unpack warps
-        const int t = threadIdx.x - 256;
-        uint32_t s = 0, ph = 0, ws = 0, wph = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int kb = 0; kb < nkb; kb++) {
-                mbar_wait(in_full + 8 * s, ph);
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------------ unpack groups
+        if constexpr (DQ) {
+            const int g = (warp - 8) >> 1;                       // group 0..3 owns k-blocks i = g (mod 4)
+            const int tg = (int)threadIdx.x - 256 - 64 * g;      // 0..63: rows tg and tg + 64 of the tile
+            uint32_t qs = g, qph = 0, ws = g, wph = 0;           // ring positions of k-block i = g
+            for (int i = g; i < total_kb; i += N_GROUPS) {
+                mbar_wait(q_full + 8 * qs, qph);
                 mbar_wait(w_empty + 8 * ws, wph ^ 1);
-                unpack_block<DQ ? QT : QT_Q4_0, BF>(smem_base + s * IN_STAGE + X_STAGE, smem_base + W_RING + ws * W_STAGE, t);
+                const uint32_t qa = smem_base + C::Q_OFF + qs * C::CHUNK, wa = smem_base + C::W_OFF + ws * W_STAGE;
+                #pragma unroll
+                for (int b = 0; b < 4; b++)                        // (row, half) = 4 ggml blocks per thread
+                    unpack_block<DQ ? QT : QT_Q4_0, BF>(qa, wa, (b & 1) * 128 + tg + 64 * (b >> 1));
                 fence_proxy_async_smem();      // st.shared (generic proxy) -> visible to UMMA (async proxy)
                 __syncwarp();
                 if (lane == 0) {
                     mbar_arrive(w_full + 8 * ws);
-                    mbar_arrive(in_empty + 8 * s);
+                    mbar_arrive(q_empty + 8 * qs);
                 }
-                if (++s == SI) { s = 0; ph ^= 1; }
-                if (++ws == SW) { ws = 0; wph ^= 1; }
+                qs += N_GROUPS; if (qs >= (uint32_t)SQ) { qs -= SQ; qph ^= 1; }
+                ws += N_GROUPS; if (ws >= (uint32_t)SW) { ws -= SW; wph ^= 1; }
             }
         }
     }
@@ -358,12 +391,12 @@ EncodeTiledFn get_encode() {
 
 template <int QT, bool BF>
 cudaError_t launch_t(const KParams& kp, int grid, cudaStream_t st) {
-    gemm_dq_kernel<QT, BF><<<grid, QT == QT_F16 ? 256 : 512, smem_bytes(QT), st>>>(kp);
+    gemm_dq_kernel<QT, BF><<<grid, QT == QT_F16 ? 256 : 512, Cfg<QT>::SMEM, st>>>(kp);
     return cudaGetLastError();
 }
 template <int QT, bool BF>
 cudaError_t set_attr() {
-    return cudaFuncSetAttribute(gemm_dq_kernel<QT, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(QT));
+    return cudaFuncSetAttribute(gemm_dq_kernel<QT, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<QT>::SMEM);
 }
 
 }  // namespace
@@ -397,6 +430,8 @@ cudaError_t gemm_init() {
 cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream, int num_sms, uint64_t* launches) {
     if (a.M <= 0) return cudaSuccess;
     if (a.N % BM || a.K % BK || !a.x_map || !a.out) return cudaErrorInvalidValue;
+    if ((unsigned long long)a.M * (unsigned long long)a.ldo >= (1ull << 32)) return cudaErrorInvalidValue;   // 32-bit element offsets
+    if ((a.epi == EPI_STORE16 || a.epi == EPI_GELU16 || a.epi == EPI_QGELU16) && (a.out_bf16 != 0) != a.operand_bf16) return cudaErrorInvalidValue;
     if (a.qtype == QT_F16 && (a.operand_bf16 || !a.w_map)) return cudaErrorInvalidValue;
     if (a.qtype != QT_F16 && !a.w_packed) return cudaErrorInvalidValue;
     KParams kp;
@@ -407,7 +442,7 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream, int num_sms, uin
     kp.bias = a.bias;
     kp.out = a.out;
     kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.ldo = a.ldo;
-    kp.epi = a.epi; kp.out_bf16 = a.out_bf16; kp.scale_cols = a.scale_cols; kp.scale = a.scale;
+    kp.epi = a.epi; kp.scale_cols = a.scale_cols; kp.scale = a.scale;
     const int n_tiles = (a.N / BM) * ((a.M + BN - 1) / BN);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
     if (launches) ++*launches;
