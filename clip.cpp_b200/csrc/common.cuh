@@ -34,6 +34,13 @@ enum Epi : int {
 // --------------------------------------------------------------------------------------------------
 CB_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// exactly one lane of a converged warp returns true (elect.sync: ptxas treats the guarded code as single-threaded)
+CB_DEVINL bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // --------------------------------------------------------------------------------------------------
 // mbarrier
 // --------------------------------------------------------------------------------------------------
@@ -143,12 +150,21 @@ constexpr uint32_t umma_idesc(bool bf16, int M, int N) {
     return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
-CB_DEVINL void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// enable-input-d predicate is a compile-time constant in each variant (folds to PT / !PT, no per-issue setp)
+CB_DEVINL void umma_f16_acc(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        "l"(desc_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+CB_DEVINL void umma_f16_init(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {   // D = A.B (overwrite)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc)
         : "memory");
 }
 // commit all previously issued tcgen05 async ops of this thread; arrives (count 1) on the mbarrier when they finish.

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             const int ft = tile % n_ft, tt = tile / n_ft;
             for (int kb = 0; kb < nkb; kb++) {
                 mbar_wait(x_empty + 8 * s, ph ^ 1);
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t dst = smem_base + s * C::XS;
                     mbar_arrive_expect_tx(x_full + 8 * s, C::XS);
                     tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, x_full + 8 * s);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 const uint8_t* src = p.w_packed + (size_t)ft * nkb * C::CHUNK;
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(q_empty + 8 * s, ph ^ 1);
-                    if (lane == 0) {
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(q_full + 8 * s, C::CHUNK);
                         bulk_load_1d(smem_base + C::Q_OFF + s * C::CHUNK, src + (size_t)kb * C::CHUNK, C::CHUNK, q_full + 8 * s);
                     }
@@ -291,33 +291,43 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        uint32_t s = 0, ph = 0, ws = 0, wph = 0;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-            const uint32_t as = it & 1, aph = (it >> 1) & 1;
-            mbar_wait(acc_empty + 8 * as, aph ^ 1);
-            tc_fence_after();
-            for (int kb = 0; kb < nkb; kb++) {
-                mbar_wait(x_full + 8 * s, ph);
-                if constexpr (DQ) mbar_wait(w_full + 8 * ws, wph);
+        // ------------------------------------------------------------------ MMA issuer: the warp walks the loop, ONE elected thread issues.
+        // The issue path per k-block must stay far below the 512 tensor cycles it feeds (4 UTCHMMA + 2-3 UTCBAR + 2 waits);
+        // descriptors are a base + stage * constant, nothing is recomputed or broadcast across lanes.
+        {
+            const uint64_t dx0 = umma_desc_k128(smem_base);
+            const uint64_t dw0 = umma_desc_k128(DQ ? smem_base + C::W_OFF : smem_base + X_STAGE);
+            constexpr uint64_t X_STEP = C::XS >> 4, W_STEP = DQ ? (W_STAGE >> 4) : (C::XS >> 4);
+            uint32_t s = 0, ph = 0, ws = 0, wph = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+                const uint32_t as = it & 1, aph = (it >> 1) & 1;
+                const uint32_t d_tmem = tmem_base + as * BN;
+                mbar_wait(acc_empty + 8 * as, aph ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t xa = smem_base + s * C::XS;
-                    const uint32_t wa = DQ ? (smem_base + C::W_OFF + ws * W_STAGE) : (xa + X_STAGE);
-                    const uint64_t da = umma_desc_k128(wa), db = umma_desc_k128(xa);
-                    #pragma unroll
-                    for (int k = 0; k < BK / 16; k++)   // advance 16 elements = 32 B = 2 descriptor units
-                        umma_f16(tmem_base + as * BN, da + 2 * k, db + 2 * k, IDESC, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(x_empty + 8 * s);
-                    if constexpr (DQ) umma_commit(w_empty + 8 * ws);
-                    if (kb == nkb - 1) umma_commit(acc_full + 8 * as);
+                for (int kb = 0; kb < nkb; kb++) {
+                    mbar_wait(x_full + 8 * s, ph);
+                    if constexpr (DQ) mbar_wait(w_full + 8 * ws, wph);
+                    tc_fence_after();
+                    const uint64_t db = dx0 + (uint64_t)s * X_STEP;
+                    const uint64_t da = dw0 + (uint64_t)(DQ ? ws : s) * W_STEP;
+                    if (elect_one()) {      // elect.sync: ptxas keeps the operands in uniform registers (no per-lane waterfall)
+                        if (kb == 0) umma_f16_init(d_tmem, da, db, IDESC);
+                        else umma_f16_acc(d_tmem, da, db, IDESC);
+                        umma_f16_acc(d_tmem, da + 2, db + 2, IDESC);      // +16 elements = +32 B = +2 descriptor units
+                        umma_f16_acc(d_tmem, da + 4, db + 4, IDESC);
+                        umma_f16_acc(d_tmem, da + 6, db + 6, IDESC);
+                        umma_commit(x_empty + 8 * s);
+                        if constexpr (DQ) umma_commit(w_empty + 8 * ws);
+                        if (kb == nkb - 1) umma_commit(acc_full + 8 * as);
+                    }
+                    __syncwarp();
+                    if (++s == SX) { s = 0; ph ^= 1; }
+                    if constexpr (DQ) { if (++ws == SW) { ws = 0; wph ^= 1; } }
                 }
-                __syncwarp();
-                if (++s == SX) { s = 0; ph ^= 1; }
-                if constexpr (DQ) { if (++ws == SW) { ws = 0; wph ^= 1; } }
             }
         }
+        __syncwarp();
     } else if (warp >= 4 && warp < 8) {
         // ------------------------------------------------------------------ epilogue
         const int fr = (warp & 3) * 32 + lane;                     // feature row of the tile == TMEM lane
