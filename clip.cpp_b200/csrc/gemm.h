@@ -16,7 +16,7 @@ bool make_tma_2d_16bit(TmaMap* out, const void* gptr, uint64_t rows, uint64_t co
                        uint32_t box_rows);
 
 constexpr int GEMM_BM = 128;   // features per tile (UMMA M / TMEM lanes)
-constexpr int GEMM_BN = 256;   // tokens per tile   (UMMA N / TMEM columns)
+constexpr int GEMM_BN = 192;   // tokens per tile   (UMMA N / TMEM columns; 2 x 192 accumulator columns + 128 A-operand columns = 512)
 constexpr int GEMM_BK = 64;
 
 struct GemmArgs {

@@ -5,28 +5,29 @@
 //
 //   Y[token, feature] = sum_k X[token, k] * W[feature, k]  (+ bias, + epilogue)
 //
-// computed "swap-AB": the WEIGHT tile is the UMMA A operand (M = 128 features = TMEM lanes), the
-// ACTIVATION tile is the B operand (N = 256 tokens = TMEM columns).  Consequences:
-//   * only 128x64 weights are unpacked per 128x256x64 MMA block (half the ALU work of the other
-//     orientation), and bias / Q-scale are per-thread constants in the epilogue;
-//   * the epilogue thread <-> feature mapping makes every global store naturally coalesced
-//     (32 lanes = 32 consecutive features of one token), no shared-memory transpose needed.
+// computed "swap-AB": the WEIGHT tile is the UMMA A operand (M = 128 features = TMEM lanes), the ACTIVATION tile is
+// the B operand (N = 192 tokens = TMEM columns).  Quantized weights never touch shared memory in unpacked form: the
+// unpack warps write the dequantised fp16/bf16 tile straight into TENSOR MEMORY (tcgen05.st) and the MMA takes its A
+// operand from TMEM (tcgen05.mma "TS" form).  Shared memory then carries only the activation tile (TMA in, UMMA out) and
+// the packed 4-8 bit blocks -- it was the binding resource of the earlier smem->smem version.
 //
 // Warp roles (persistent CTA, 1 per SM, 512 threads; 256 for unquantized f16 weights):
-//   warp 0      X producer: activation box [256 tokens x 64 k] (UTMALDG, 128B swizzle)            -> x_full[s]
+//   warp 0      X producer: activation box [192 tokens x 64 k] (UTMALDG, 128B swizzle)            -> x_full[s]
 //   warp 3      Q producer: ONE 1-D bulk copy (UBLKCP) per k-block of the packed 32-weight blocks + scales of
 //               the [128 x 64] weight tile (wpack.h); runs up to 8 k-blocks ahead                  -> q_full[s]
-//   warps 8-15  unpack, 4 groups x 2 warps; group g owns k-blocks i = g (mod 4), so four k-blocks are being
-//               unpacked concurrently (hides mbarrier / proxy-fence latency): packed q4_0/q4_1/q5_0/q5_1/q8_0
-//               -> fp16/bf16 A tile in the UMMA K-major/128B-swizzle layout (st.shared.v4)        -> w_full[j]
-//   warp 1      one thread issues tcgen05.mma (M128 N256 K16, kind::f16), fp32 accumulators in TMEM,
-//               tcgen05.commit releases the X / W stages and signals the epilogue
+//   warps 8-15  unpack, 2 groups x 4 warps (one warp per TMEM lane quarter); group g owns k-blocks i = g (mod 2):
+//               thread = one weight row x 64 k: ld.shared packed q4_0/q4_1/q5_0/q5_1/q8_0 -> 32 registers of 16-bit
+//               pairs -> tcgen05.st.32x32b.x32 into A stage (i mod 4)                               -> a_full[j]
+//   warp 1      one elected thread issues tcgen05.mma (M128 N192 K16, kind::f16, A from TMEM, B from smem), fp32
+//               accumulators in TMEM; tcgen05.commit releases the X / A stages and signals the epilogue
 //   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / scale / GELU / residual -> coalesced global stores;
-//               double-buffered accumulators (2 x 256 TMEM columns) overlap it with the next tile's MMAs
-//   warp 2      TMEM alloc / dealloc
+//               double-buffered accumulators (2 x 192 TMEM columns) overlap it with the next tile's MMAs
+//   warp 2      TMEM alloc / dealloc   (TMEM map: acc0 [0,192) acc1 [192,384) A stages [384 + 32 j), j < 4)
 //
+// Unquantized (f16 / f32-rounded-to-f16) weights use the plain SS form: warp 0 TMA-loads X and W tiles.
 // Algorithmic bytes per launch: packed W once + X once + Y once; FLOPs = 2*M*N*K.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -37,11 +38,15 @@ namespace cb {
 namespace {
 
 constexpr int BM = GEMM_BM, BN = GEMM_BN, BK = GEMM_BK;
-constexpr int X_STAGE = BN * BK * 2;   // 32768 B
-constexpr int W_STAGE = BM * BK * 2;   // 16384 B
-constexpr int N_GROUPS = 4;            // unpack groups (2 warps each)
+constexpr int X_STAGE = BN * BK * 2;   // 24576 B
+constexpr int W_STAGE = BM * BK * 2;   // 16384 B (f16 path only)
+constexpr int N_GROUPS = 2;            // unpack groups (4 warps each)
+constexpr int NA = 4;                  // A-operand stages in TMEM (32 columns each)
 constexpr int N_EPI_WARPS = 4;
-constexpr uint32_t TMEM_COLS = 512;    // 2 accumulator stages x 256 columns
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t A_COL0 = 2 * BN;    // first TMEM column of the A stages
+static_assert(2 * BN + NA * 32 <= 512, "TMEM budget");
+static_assert(X_STAGE % 1024 == 0, "swizzled stage alignment");
 
 __host__ __device__ constexpr uint32_t chunk_bytes(int qt) {
     return qt == 2 ? 4608u : qt == 3 ? 5120u : qt == 6 ? 5632u : qt == 7 ? 6144u : qt == 8 ? 8704u : 0u;
@@ -51,16 +56,14 @@ template <int QT>
 struct Cfg {
     static constexpr bool DQ = (QT != QT_F16);
     static constexpr uint32_t CHUNK = chunk_bytes(QT);
-    static constexpr int SX = DQ ? 3 : 4;                              // X ring (f16: X + W per stage)
-    static constexpr int SW = DQ ? (QT == QT_Q8_0 ? 4 : 5) : 0;        // unpacked-weight ring
-    static constexpr int SQ = DQ ? (QT == QT_Q8_0 ? 6 : 8) : 0;        // packed-weight ring
+    static constexpr int SX = DQ ? 6 : 5;                              // X ring (f16: X + W per stage)
+    static constexpr int SQ = DQ ? 8 : 0;                              // packed-weight ring
     static constexpr uint32_t XS = DQ ? (uint32_t)X_STAGE : (uint32_t)(X_STAGE + W_STAGE);
-    static constexpr uint32_t W_OFF = SX * XS;
-    static constexpr uint32_t Q_OFF = W_OFF + SW * W_STAGE;
+    static constexpr uint32_t Q_OFF = SX * XS;
     static constexpr uint32_t BAR_OFF = Q_OFF + SQ * CHUNK;
     static constexpr uint32_t SMEM = BAR_OFF + 512 /*barriers*/ + 1024 /*align slack*/;
     static_assert(SMEM <= 232448, "shared memory plan exceeds 227 KB");
-    static_assert(!DQ || (SW >= N_GROUPS && SQ >= N_GROUPS), "rings must cover the concurrent unpack groups");
+    static_assert(XS % 1024 == 0, "stage alignment");
 };
 
 struct KParams {
@@ -72,6 +75,7 @@ struct KParams {
     int M, N, K, ldo;
     int epi, scale_cols;
     float scale;
+    int dbg;   // experiment switches (env CLIP_B200_GEMM_DBG, tools only): 1 skip unpack math, 2 skip X loads, 4 skip Q loads, 8 skip epilogue
 };
 
 // explicit .shared accesses on 32-bit shared-window addresses (generic ld/st would cost an address-space check)
@@ -91,15 +95,13 @@ CB_DEVINL uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return r;
 }
 
-// Unpack the 32-weight ggml block owned by thread t (= half*128 + row) of a [128 x 64] tile into the
-// UMMA A-operand image: row r at (r/8)*1024 + (r%8)*128, 16-byte chunk c at position c ^ (r%8).
-// Arithmetic matches dequantize_row_q* (ggml/src/ggml.c:1496-1606): (q - zero) * d  or  q * d + m, with the
-// integer part exact (magic-number int->float) and ONE rounding of the product to the operand type.
+// Unpack the 32-weight ggml block t (= half*128 + row) of a packed [128 x 64] tile (wpack.h) into 16 registers holding
+// the 32 weights as adjacent 16-bit pairs in k order (out[c] = {w[2c], w[2c+1]}) -- exactly one TMEM row segment of the
+// UMMA A operand.  Arithmetic matches dequantize_row_q* (ggml/src/ggml.c:1496-1606): (q - zero) * d  or  q * d + m,
+// with the integer part exact (magic-number int->float) and ONE rounding of the product to the operand type.
 template <int QT, bool BF>
-CB_DEVINL void unpack_block(uint32_t q, uint32_t w, int t) {
+CB_DEVINL void unpack_block(uint32_t q, int t, uint32_t* __restrict__ out) {
     using P = P2<BF>;
-    const int half = t >> 7, r = t & 127, sw = r & 7;
-    const uint32_t row = w + (r >> 3) * 1024 + sw * 128;
     if constexpr (QT == QT_Q8_0) {
         const uint4 qa = lds128(q + 16 * t), qb = lds128(q + 4096 + 16 * t);
         const uint32_t d2 = P::splat_from_f16bits(lds16(q + 8192 + 2 * t));
@@ -121,7 +123,7 @@ CB_DEVINL void unpack_block(uint32_t q, uint32_t w, int t) {
                     v[2 * h + 1] = P::mul(P::sub(m23, c23), d2);
                 }
             }
-            sts128(row + (((4 * half + c) ^ sw) << 4), v[0], v[1], v[2], v[3]);
+            out[4 * c + 0] = v[0]; out[4 * c + 1] = v[1]; out[4 * c + 2] = v[2]; out[4 * c + 3] = v[3];
         }
     } else {
         constexpr bool Q5 = (QT == QT_Q5_0 || QT == QT_Q5_1);
@@ -156,12 +158,12 @@ CB_DEVINL void unpack_block(uint32_t q, uint32_t w, int t) {
                 const uint32_t qv = P::sub(x, C2);
                 v[i] = AFFINE ? P::fma(qv, d2, m2) : P::mul(qv, d2);
             }
-            sts128(row + (((4 * half + j) ^ sw) << 4), v[0], v[1], v[2], v[3]);
+            out[4 * j + 0] = v[0]; out[4 * j + 1] = v[1]; out[4 * j + 2] = v[2]; out[4 * j + 3] = v[3];
         }
     }
 }
 
-// Epilogue of one [128 features x 256 tokens] accumulator: this thread owns feature n (TMEM lane) and walks the token
+// Epilogue of one [128 features x 192 tokens] accumulator: this thread owns feature n (TMEM lane) and walks the token
 // columns 32 at a time.  For a fixed token the 32 lanes of a warp hold 32 consecutive features -> every global access
 // below is one fully coalesced 64-B (16-bit) or 128-B (fp32) request.  Specialised per epilogue kind at compile time;
 // element offsets are 32-bit (host checks M*ldo < 2^32) so each access costs one IADD + one IMAD.WIDE.
@@ -221,7 +223,7 @@ template <int QT, bool BF>
 __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(const __grid_constant__ KParams p) {
     using C = Cfg<QT>;
     constexpr bool DQ = C::DQ;
-    constexpr int SX = C::SX, SW = DQ ? C::SW : 1, SQ = DQ ? C::SQ : 1;
+    constexpr int SX = C::SX, SQ = DQ ? C::SQ : 1;
     constexpr uint32_t IDESC = umma_idesc(BF, BM, BN);
 
     extern __shared__ uint8_t smem_raw[];
@@ -230,16 +232,16 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
     const uint32_t bars = smem_base + C::BAR_OFF;
     // barrier slots (8 B each)
     const uint32_t x_full = bars, x_empty = x_full + 8 * SX, q_full = x_empty + 8 * SX, q_empty = q_full + 8 * SQ,
-                   w_full = q_empty + 8 * SQ, w_empty = w_full + 8 * SW, acc_full = w_empty + 8 * SW, acc_empty = acc_full + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 16 * SX + 16 * SQ + 16 * SW + 32);
-    static_assert(16 * C::SX + 16 * (DQ ? C::SQ : 1) + 16 * (DQ ? C::SW : 1) + 32 + 4 <= 512, "barrier area");
+                   a_full = q_empty + 8 * SQ, a_empty = a_full + 8 * NA, acc_full = a_empty + 8 * NA, acc_empty = acc_full + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::BAR_OFF + 16 * SX + 16 * SQ + 16 * NA + 32);
+    static_assert(16 * C::SX + 16 * (DQ ? C::SQ : 1) + 16 * NA + 32 + 4 <= 512, "barrier area");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < SX; i++) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); }
-        for (int i = 0; i < SQ; i++) { mbar_init(q_full + 8 * i, 1); mbar_init(q_empty + 8 * i, 2); }
-        for (int i = 0; i < SW; i++) { mbar_init(w_full + 8 * i, 2); mbar_init(w_empty + 8 * i, 1); }
+        for (int i = 0; i < SQ; i++) { mbar_init(q_full + 8 * i, 1); mbar_init(q_empty + 8 * i, 4); }
+        for (int i = 0; i < NA; i++) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, 1); }
         for (int i = 0; i < 2; i++) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, N_EPI_WARPS); }
         mbar_fence_init();
         tma_prefetch_desc(&p.tm_x);
@@ -264,9 +266,12 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 mbar_wait(x_empty + 8 * s, ph ^ 1);
                 if (elect_one()) {
                     const uint32_t dst = smem_base + s * C::XS;
-                    mbar_arrive_expect_tx(x_full + 8 * s, C::XS);
-                    tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, x_full + 8 * s);
-                    if constexpr (!DQ) tma_load_2d(dst + X_STAGE, &p.tm_w, kb * BK, ft * BM, x_full + 8 * s);
+                    if (p.dbg & 2) mbar_arrive(x_full + 8 * s);
+                    else {
+                        mbar_arrive_expect_tx(x_full + 8 * s, C::XS);
+                        tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, x_full + 8 * s);
+                        if constexpr (!DQ) tma_load_2d(dst + X_STAGE, &p.tm_w, kb * BK, ft * BM, x_full + 8 * s);
+                    }
                 }
                 __syncwarp();
                 if (++s == SX) { s = 0; ph ^= 1; }
@@ -282,8 +287,11 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(q_empty + 8 * s, ph ^ 1);
                     if (elect_one()) {
+                        if (p.dbg & 4) mbar_arrive(q_full + 8 * s);
+                        else {
                         mbar_arrive_expect_tx(q_full + 8 * s, C::CHUNK);
                         bulk_load_1d(smem_base + C::Q_OFF + s * C::CHUNK, src + (size_t)kb * C::CHUNK, C::CHUNK, q_full + 8 * s);
+                        }
                     }
                     __syncwarp();
                     if (++s == SQ) { s = 0; ph ^= 1; }
@@ -291,43 +299,49 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer: the warp walks the loop, ONE elected thread issues.
-        // The issue path per k-block must stay far below the 512 tensor cycles it feeds (4 UTCHMMA + 2-3 UTCBAR + 2 waits);
-        // descriptors are a base + stage * constant, nothing is recomputed or broadcast across lanes.
-        {
-            const uint64_t dx0 = umma_desc_k128(smem_base);
-            const uint64_t dw0 = umma_desc_k128(DQ ? smem_base + C::W_OFF : smem_base + X_STAGE);
-            constexpr uint64_t X_STEP = C::XS >> 4, W_STEP = DQ ? (W_STAGE >> 4) : (C::XS >> 4);
-            uint32_t s = 0, ph = 0, ws = 0, wph = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-                const uint32_t as = it & 1, aph = (it >> 1) & 1;
-                const uint32_t d_tmem = tmem_base + as * BN;
-                mbar_wait(acc_empty + 8 * as, aph ^ 1);
+        // ------------------------------------------------------------------ MMA issuer: the warp walks the loop, ONE elected
+        // thread issues (elect.sync keeps descriptors in uniform registers: 4 UTCHMMA + 2-3 UTCBAR back to back per k-block)
+        const uint64_t dx0 = umma_desc_k128(smem_base);
+        const uint64_t dw0 = umma_desc_k128(smem_base + X_STAGE);    // f16 path: W tile follows the X tile in each stage
+        constexpr uint64_t X_STEP = C::XS >> 4;
+        uint32_t s = 0, ph = 0, sa = 0, pa = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            const uint32_t d_tmem = tmem_base + as * BN;
+            mbar_wait(acc_empty + 8 * as, aph ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; kb++) {
+                mbar_wait(x_full + 8 * s, ph);
+                if constexpr (DQ) mbar_wait(a_full + 8 * sa, pa);
                 tc_fence_after();
-                for (int kb = 0; kb < nkb; kb++) {
-                    mbar_wait(x_full + 8 * s, ph);
-                    if constexpr (DQ) mbar_wait(w_full + 8 * ws, wph);
-                    tc_fence_after();
-                    const uint64_t db = dx0 + (uint64_t)s * X_STEP;
-                    const uint64_t da = dw0 + (uint64_t)(DQ ? ws : s) * W_STEP;
-                    if (elect_one()) {      // elect.sync: ptxas keeps the operands in uniform registers (no per-lane waterfall)
+                const uint64_t db = dx0 + (uint64_t)s * X_STEP;
+                if (elect_one()) {
+                    if constexpr (DQ) {
+                        const uint32_t a_t = tmem_base + A_COL0 + sa * 32;      // 16 k = 8 TMEM columns per MMA step
+                        if (kb == 0) umma_f16_ts_init(d_tmem, a_t, db, IDESC);
+                        else umma_f16_ts_acc(d_tmem, a_t, db, IDESC);
+                        umma_f16_ts_acc(d_tmem, a_t + 8, db + 2, IDESC);          // B: +16 elements = +32 B = +2 descriptor units
+                        umma_f16_ts_acc(d_tmem, a_t + 16, db + 4, IDESC);
+                        umma_f16_ts_acc(d_tmem, a_t + 24, db + 6, IDESC);
+                        umma_commit(x_empty + 8 * s);
+                        umma_commit(a_empty + 8 * sa);
+                    } else {
+                        const uint64_t da = dw0 + (uint64_t)s * X_STEP;
                         if (kb == 0) umma_f16_init(d_tmem, da, db, IDESC);
                         else umma_f16_acc(d_tmem, da, db, IDESC);
-                        umma_f16_acc(d_tmem, da + 2, db + 2, IDESC);      // +16 elements = +32 B = +2 descriptor units
+                        umma_f16_acc(d_tmem, da + 2, db + 2, IDESC);
                         umma_f16_acc(d_tmem, da + 4, db + 4, IDESC);
                         umma_f16_acc(d_tmem, da + 6, db + 6, IDESC);
                         umma_commit(x_empty + 8 * s);
-                        if constexpr (DQ) umma_commit(w_empty + 8 * ws);
-                        if (kb == nkb - 1) umma_commit(acc_full + 8 * as);
                     }
-                    __syncwarp();
-                    if (++s == SX) { s = 0; ph ^= 1; }
-                    if constexpr (DQ) { if (++ws == SW) { ws = 0; wph ^= 1; } }
+                    if (kb == nkb - 1) umma_commit(acc_full + 8 * as);
                 }
+                __syncwarp();
+                if (++s == SX) { s = 0; ph ^= 1; }
+                if constexpr (DQ) { if (++sa == NA) { sa = 0; pa ^= 1; } }
             }
         }
-        __syncwarp();
     } else if (warp >= 4 && warp < 8) {
         // ------------------------------------------------------------------ epilogue
         const int fr = (warp & 3) * 32 + lane;                     // feature row of the tile == TMEM lane
@@ -343,7 +357,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             tc_fence_after();
             const int tok0 = tt * BN;
             const uint32_t acc_addr = lane_addr + as * BN;
-            switch (p.epi) {
+            if (!(p.dbg & 8)) switch (p.epi) {
             case EPI_STORE16: epilogue_tile<EPI_STORE16, BF>(p, acc_addr, tok0, n, bias, mul); break;
             case EPI_GELU16: epilogue_tile<EPI_GELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
             case EPI_QGELU16: epilogue_tile<EPI_QGELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
@@ -355,26 +369,32 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             if (lane == 0) mbar_arrive(acc_empty + 8 * as);
         }
     } else if (warp >= 8) {
-        // ------------------------------------------------------------------ unpack groups
+        // ------------------------------------------------------------------ unpack groups: registers -> TMEM A stages
         if constexpr (DQ) {
-            const int g = (warp - 8) >> 1;                       // group 0..3 owns k-blocks i = g (mod 4)
-            const int tg = (int)threadIdx.x - 256 - 64 * g;      // 0..63: rows tg and tg + 64 of the tile
-            uint32_t qs = g, qph = 0, ws = g, wph = 0;           // ring positions of k-block i = g
+            const int g = (warp - 8) >> 2;                        // group 0..1 owns k-blocks i = g (mod 2)
+            const int row = (warp & 3) * 32 + lane;               // weight row of the tile == TMEM lane (warp%4 = lane quarter)
+            const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0;
+            uint32_t qs = g, qph = 0, sa = g, pa = 0;             // ring positions of k-block i = g
             for (int i = g; i < total_kb; i += N_GROUPS) {
                 mbar_wait(q_full + 8 * qs, qph);
-                mbar_wait(w_empty + 8 * ws, wph ^ 1);
-                const uint32_t qa = smem_base + C::Q_OFF + qs * C::CHUNK, wa = smem_base + C::W_OFF + ws * W_STAGE;
-                #pragma unroll
-                for (int b = 0; b < 4; b++)                        // (row, half) = 4 ggml blocks per thread
-                    unpack_block<DQ ? QT : QT_Q4_0, BF>(qa, wa, (b & 1) * 128 + tg + 64 * (b >> 1));
-                fence_proxy_async_smem();      // st.shared (generic proxy) -> visible to UMMA (async proxy)
+                mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                tc_fence_after();
+                const uint32_t qa = smem_base + C::Q_OFF + qs * C::CHUNK;
+                if (!(p.dbg & 1)) {
+                    uint32_t v[32];
+                    unpack_block<DQ ? QT : QT_Q4_0, BF>(qa, row, v);              // k  0..31 of this row
+                    unpack_block<DQ ? QT : QT_Q4_0, BF>(qa, 128 + row, v + 16);   // k 32..63
+                    tmem_st_32x32(a_lane + sa * 32, v);
+                    tmem_st_wait();
+                }
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(w_full + 8 * ws);
+                    mbar_arrive(a_full + 8 * sa);
                     mbar_arrive(q_empty + 8 * qs);
                 }
                 qs += N_GROUPS; if (qs >= (uint32_t)SQ) { qs -= SQ; qph ^= 1; }
-                ws += N_GROUPS; if (ws >= (uint32_t)SW) { ws -= SW; wph ^= 1; }
+                sa += N_GROUPS; if (sa >= (uint32_t)NA) { sa -= NA; pa ^= 1; }
             }
         }
     }
@@ -453,6 +473,8 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream, int num_sms, uin
     kp.out = a.out;
     kp.M = a.M; kp.N = a.N; kp.K = a.K; kp.ldo = a.ldo;
     kp.epi = a.epi; kp.scale_cols = a.scale_cols; kp.scale = a.scale;
+    static const int dbg_env = getenv("CLIP_B200_GEMM_DBG") ? atoi(getenv("CLIP_B200_GEMM_DBG")) : 0;
+    kp.dbg = dbg_env;
     const int n_tiles = (a.N / BM) * ((a.M + BN - 1) / BN);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
     if (launches) ++*launches;
