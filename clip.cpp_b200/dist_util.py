@@ -1,0 +1,38 @@
+"""Multi-GPU plumbing for the encode path: one process per GPU, images / sequences shard
+embarrassingly, weights are replicated, and the ONLY exchange is one all-gather of the final embeddings per call
+(NCCL over NVLink on GPUs; the same code runs on gloo for the CPU tests).  torch.distributed is plumbing only."""
+from __future__ import annotations
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous shards of n // world items; the last rank takes the remainder."""
+    per = n // world
+    lo = rank * per
+    hi = n if rank == world - 1 else lo + per
+    return lo, hi
+
+
+def all_gather_rows(dist, local, n_total: int, world: int):
+    """local: [n_local, d] tensor on this rank -> [n_total, d] on every rank (ragged shards are padded to the largest)."""
+    import torch
+    per, last = n_total // world, n_total - (world - 1) * (n_total // world)
+    width = max(per, last)
+    d = local.shape[1]
+    pad = torch.zeros((width, d), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * width, d), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    rows = [out[r * width: r * width + (last if r == world - 1 else per)] for r in range(world)]
+    return torch.cat(rows, 0)
+
+
+def zero_shot_sharded(dist, rank, world, img_local, txt_local, n_txt_total, top_k):
+    """configs[4] pattern: each rank holds its image shard and its LABEL shard; text embeddings are all-gathered
+    (the one collective), logits + softmax_with_sorting arithmetic (clip.cpp:1591-1622) run locally per image."""
+    import torch
+    txt = all_gather_rows(dist, txt_local, n_txt_total, world) if world > 1 else txt_local
+    logits = img_local @ txt.T
+    e = torch.exp(logits.double()).float() + 1e-9
+    p = (e / e.double().sum(1, keepdim=True)).float()
+    scores, idx = torch.sort(p, dim=1, descending=True, stable=True)
+    return scores[:, :top_k], idx[:, :top_k]

@@ -1,0 +1,122 @@
+"""Host-side members of the interface (no GPU): file quantizer, weight re-tiling, tokenizer, preprocess -- each
+checked bit-exactly against vectors produced by the reference (tests/golden, oracle/_ref) and, when the reference
+library is present, against it live."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import binding as bd
+import ref_run
+import synth_gguf as sg
+from _util import FTYPES, GOLDEN, check_sha, golden, model_file
+
+HOST = json.load(open(os.path.join(GOLDEN, "host_ops.json")))
+
+
+@pytest.mark.parametrize("ft", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_quantize_is_byte_identical_to_reference(prod, ft):
+    """clip_model_quantize (clip.cpp:1661-1844): the sha256 in the fixture is of the file the REFERENCE's quantizer wrote."""
+    g = golden("tiny")
+    path = sg.model_path("tiny", 1234, ft) + ".check"
+    assert prod.quantize(model_file("tiny", "f16", prod), path, FTYPES[ft])
+    try:
+        check_sha(path, g["sha_" + ft])
+    finally:
+        os.remove(path)
+
+
+def test_quantize_rejects_bad_arguments(prod):
+    assert not prod.quantize(model_file("tiny", "f16", prod), "/tmp/x.gguf", 5)       # unknown type
+    assert not prod.quantize("/nonexistent.gguf", "/tmp/x.gguf", 2)
+    assert not prod.quantize(model_file("tiny", "q4_0", prod), "/tmp/x.gguf", 2)      # already quantized
+
+
+@pytest.mark.parametrize("ft", ["q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
+def test_weight_retiling_is_lossless(prod, ft):
+    """wpack.h: the TMA-friendly re-tiling keeps every quant and every fp16 scale bit (round trip on random blocks)."""
+    import oracle as orc
+    rng = np.random.default_rng(5)
+    N, K = 256, 192
+    raw = orc.quantize_rows(FTYPES[ft], (rng.standard_normal((N, K)) * 0.1).astype(np.float32))
+    buf = np.frombuffer(raw, np.uint8)
+    assert prod.lib.clip_b200_debug_repack_roundtrip(FTYPES[ft], buf.ctypes.data, N, K) == 0
+    assert prod.lib.clip_b200_debug_repack_roundtrip(FTYPES[ft], buf.ctypes.data, 100, K) != 0     # N % 128 != 0 is refused
+
+
+def _tokenize(prod, model, text):
+    out = (C.c_int32 * 512)()
+    n = prod.lib.clip_b200_debug_tokenize(model.encode(), text.encode("latin1"), out, 512)
+    assert n >= 2
+    return [int(out[i]) for i in range(n)]
+
+
+def test_tokenizer_matches_reference_golden(prod):
+    model = model_file("tiny", "f16", prod)
+    check_sha(model, HOST["model_sha"])
+    for text, ids in HOST["tokens"].items():
+        assert _tokenize(prod, model, text) == ids, repr(text)
+
+
+def _synth_u8(nx, ny, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = rng.integers(0, 256, size=(ny // 8 + 2, nx // 8 + 2, 3)).astype(np.float32)
+    img = np.kron(base, np.ones((8, 8, 1), np.float32))[:ny, :nx]
+    img += rng.normal(0, 12, size=img.shape).astype(np.float32)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def _preprocess(prod, u8, S=64):
+    mean = np.array([0.48145466, 0.4578275, 0.40821073], np.float32)
+    std = np.array([0.26862954, 0.26130258, 0.27577711], np.float32)
+    out = np.empty((S, S, 3), np.float32)
+    fp = C.POINTER(C.c_float)
+    rc = prod.lib.clip_b200_debug_preprocess(u8.ctypes.data_as(C.POINTER(C.c_uint8)), u8.shape[1], u8.shape[0], S,
+                                             mean.ctypes.data_as(fp), std.ctypes.data_as(fp), out.ctypes.data_as(fp))
+    assert rc == 0
+    return out
+
+
+def test_preprocess_matches_reference_golden_bit_exactly(prod):
+    for e in HOST["preprocess"]:
+        out = _preprocess(prod, _synth_u8(e["nx"], e["ny"], e["seed"]))
+        assert hashlib.sha256(out.tobytes()).hexdigest() == e["sha256"], e
+
+
+@pytest.mark.skipif(not ref_run.available(), reason="oracle/_ref not built")
+def test_tokenizer_and_preprocess_match_live_reference(prod):
+    import subprocess, sys, tempfile
+    model = model_file("tiny", "f16", prod)
+    texts = ["the red apple isn't a dog", "  double  spaces and 42 numbers!!", "mixed'case I'LL"]
+    u8 = _synth_u8(123, 77, 99)
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import binding as bd; r = bd.ClipLib(bd.REF_LIB); c = r.load(%r, 0);"
+            "print(json.dumps({'tok': [[int(v) for v in r.tokenize(c, t)] for t in %r], 'pre': r.preprocess(c, np.load(sys.argv[1])).ravel().tolist()}))"
+            % (os.path.join(os.path.dirname(GOLDEN), "..", "clip.cpp_b200"), model, texts))
+    with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+        np.save(f.name, u8)
+        res = json.loads(subprocess.run([sys.executable, "-c", code, f.name], capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
+    for t, ids in zip(texts, res["tok"]):
+        assert _tokenize(prod, model, t) == ids
+    assert np.array_equal(_preprocess(prod, u8).ravel(), np.array(res["pre"], np.float32))
+
+
+def test_scoring_helpers_match_reference_arithmetic(prod):
+    """clip_similarity_score (clip.cpp:1525-1532) and softmax_with_sorting (clip.cpp:1591-1622: no max subtraction, +1e-9)."""
+    fp = C.POINTER(C.c_float)
+    rng = np.random.default_rng(3)
+    a, b = rng.standard_normal(512).astype(np.float32), rng.standard_normal(512).astype(np.float32)
+    acc = np.float32(0)
+    for x, y in zip(a, b):
+        acc = np.float32(acc + np.float32(x * y))
+    assert prod.lib.clip_similarity_score(a.ctypes.data_as(fp), b.ctypes.data_as(fp), 512) == pytest.approx(float(acc), rel=1e-6)
+    s = rng.standard_normal(10).astype(np.float32)
+    arr, scores, idx = s.copy(), np.empty(10, np.float32), np.empty(10, np.int32)
+    assert prod.lib.softmax_with_sorting(arr.ctypes.data_as(fp), 10, scores.ctypes.data_as(fp), idx.ctypes.data_as(C.POINTER(C.c_int)))
+    e = (np.exp(s.astype(np.float64)) + 1e-9).astype(np.float32)
+    p = (e / e.astype(np.float64).sum()).astype(np.float32)
+    assert np.array_equal(idx, np.argsort(-p, kind="stable"))
+    assert np.allclose(scores, p[idx], rtol=1e-6)
+    assert not prod.lib.softmax_with_sorting(arr.ctypes.data_as(fp), 0, scores.ctypes.data_as(fp), idx.ctypes.data_as(C.POINTER(C.c_int)))
