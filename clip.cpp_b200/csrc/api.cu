@@ -206,6 +206,7 @@ bool load_blocks(clip_ctx* c, const GgufFile& g, const char* p, Tower& tw) {
 
 bool check_geometry(const char* what, const Tower& t) {
     if (t.heads <= 0 || t.hidden % t.heads || t.hidden / t.heads != 64) { set_err(std::string(what) + ": head_dim must be 64 (hidden " + std::to_string(t.hidden) + ", heads " + std::to_string(t.heads) + ")"); return false; }
+    if (t.hidden > 2048) { set_err(std::string(what) + ": hidden size > 2048 is not supported by the register-resident LayerNorm"); return false; }
     if (t.hidden % 128 || t.ff % 128 || t.proj % 128) { set_err(std::string(what) + ": hidden/ff/projection sizes must be multiples of 128"); return false; }
     return true;
 }
@@ -225,7 +226,7 @@ bool ensure_ws(clip_ctx* c, Tower& tw, int items, int T, bool vision) {
     const int h = tw.hidden;
     w.cap_items = items; w.T = T; w.cap_rows = items * T;
     const size_t rows = (size_t)w.cap_rows;
-    if (!dev_alloc(c, &w.x, rows * h) || !dev_alloc(c, &w.a, rows * h) || !dev_alloc(c, &w.qkv, rows * 3 * h) ||
+    if (!dev_alloc(c, &w.x, rows * h) || !dev_alloc(c, &w.a, rows * h) || !dev_alloc(c, &w.d, rows * h) || !dev_alloc(c, &w.qkv, rows * 3 * h) ||
         !dev_alloc(c, &w.g, rows * tw.ff) || !dev_alloc(c, &w.sel16, (size_t)items * h) || !dev_alloc(c, &w.sel32, (size_t)items * h) ||
         !dev_alloc(c, &w.proj32, (size_t)items * tw.proj)) return false;
     bool ok = make_tma_2d_16bit(&w.map_a, w.a, rows, h, h, GEMM_BN) && make_tma_2d_16bit(&w.map_g, w.g, rows, tw.ff, tw.ff, GEMM_BN) &&
@@ -260,18 +261,22 @@ bool run_linear(clip_ctx* c, const Linear& L, const TmaMap* xmap, const void* xp
 
 // The per-layer schedule shared by both towers (clip.cpp:1064-1143 text, 1342-1423 vision).
 bool run_blocks(clip_ctx* c, Tower& tw, int nseq, int T, bool causal) {
+    // Residual adds are deferred: each branch GEMM (out-proj, FC2) stores its output 16-bit into w.d and the NEXT LayerNorm
+    // applies x += d while it reads x anyway.  On return one delta (the last FC2) is still pending in w.d.
     Workspace& w = tw.ws;
     const int M = nseq * T, h = tw.hidden;
     const int bf = c->operand_bf16 ? 1 : 0;
     const float qscale = 1.0f / sqrtf(64.0f);
+    bool pending = false;
     for (auto& l : tw.L) {
-        { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln1_g, l.ln1_b, w.a, bf, c->stream); }
+        { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln1_g, l.ln1_b, pending ? w.d : nullptr, w.a, bf, c->stream); }
         if (!run_linear(c, l.qkv, &w.map_a, w.a, bf, M, w.qkv, 3 * h, EPI_STORE16, bf, h, qscale)) return false;
         { Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, c->stream); }
-        if (!run_linear(c, l.out, &w.map_a, w.a, bf, M, w.x, h, EPI_RESID32, 0)) return false;
-        { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln2_g, l.ln2_b, w.a, bf, c->stream); }
+        if (!run_linear(c, l.out, &w.map_a, w.a, bf, M, w.d, h, EPI_STORE16, bf)) return false;
+        { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln2_g, l.ln2_b, w.d, w.a, bf, c->stream); }
         if (!run_linear(c, l.fc1, &w.map_a, w.a, bf, M, w.g, tw.ff, c->use_gelu ? EPI_GELU16 : EPI_QGELU16, bf)) return false;
-        if (!run_linear(c, l.fc2, &w.map_g, w.g, bf, M, w.x, h, EPI_RESID32, 0)) return false;
+        if (!run_linear(c, l.fc2, &w.map_g, w.g, bf, M, w.d, h, EPI_STORE16, bf)) return false;
+        pending = true;
     }
     CK(cudaGetLastError());
     return true;
@@ -288,7 +293,7 @@ bool vision_forward(clip_ctx* c, const float* d_pixels, int nb, float* d_out, bo
     { Scope s(c, K_OTHER); launch_assemble_preln(w.patch32, tw.class_embd, tw.pos, nb, tw.T, h, tw.eps, tw.pre_g, tw.pre_b, w.x, c->stream); }
     if (!run_blocks(c, tw, nb, tw.T, false)) return false;
     // CLS rows -> post-LN -> projection -> (L2 norm)   (clip.cpp:1426-1455)
-    { Scope s(c, K_LN); launch_layernorm(w.x, (size_t)tw.T * h, nb, h, tw.eps, tw.post_g, tw.post_b, w.sel16, bf, c->stream); }
+    { Scope s(c, K_LN); launch_layernorm(w.x, (size_t)tw.T * h, nb, h, tw.eps, tw.post_g, tw.post_b, tw.layers ? w.d : nullptr, w.sel16, bf, c->stream); }
     if (!run_linear(c, tw.proj_w, &w.map_sel, w.sel16, bf, nb, w.proj32, tw.proj, EPI_STORE32, 0)) return false;
     { Scope s(c, K_OTHER); launch_l2norm(w.proj32, d_out, nb, tw.proj, normalize ? 1 : 0, c->stream); }
     CK(cudaGetLastError());
@@ -303,8 +308,8 @@ bool text_forward(clip_ctx* c, int nb, int T, float* d_out, bool normalize) {
     { Scope s(c, K_OTHER); launch_text_embed(w.ids, tw.tok, tw.pos, nb, T, h, tw.n_vocab, w.x, c->stream); }
     if (!run_blocks(c, tw, nb, T, true)) return false;
     // final LN is row-wise, so LN(select(EOT)) == select(LN(all)) (clip.cpp:1146-1155)
-    { Scope s(c, K_OTHER); launch_gather_rows(w.x, w.sel32, nb, h, T, w.last, c->stream); }
-    { Scope s(c, K_LN); launch_layernorm(w.sel32, h, nb, h, tw.eps, tw.post_g, tw.post_b, w.sel16, bf, c->stream); }
+    { Scope s(c, K_OTHER); launch_gather_rows(w.x, w.sel32, nb, h, T, w.last, tw.layers ? w.d : nullptr, bf, c->stream); }
+    { Scope s(c, K_LN); launch_layernorm(w.sel32, h, nb, h, tw.eps, tw.post_g, tw.post_b, nullptr, w.sel16, bf, c->stream); }
     if (!run_linear(c, tw.proj_w, &w.map_sel, w.sel16, bf, nb, w.proj32, tw.proj, EPI_STORE32, 0)) return false;
     { Scope s(c, K_OTHER); launch_l2norm(w.proj32, d_out, nb, tw.proj, normalize ? 1 : 0, c->stream); }
     CK(cudaGetLastError());

@@ -46,8 +46,16 @@ CB_DEVINL void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint
                      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 template <bool BF>
-CB_DEVINL uint32_t pack2(float lo, float hi) {
-    return (uint32_t)P2<BF>::from_float(lo) | ((uint32_t)P2<BF>::from_float(hi) << 16);
+CB_DEVINL uint32_t pack2(float lo, float hi) {      // one F2FP: two fp32 -> packed 16-bit pair (lo in the low half)
+    uint32_t r;
+    if constexpr (BF) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+CB_DEVINL float ex2(float x) {                       // single MUFU.EX2 (exp2f() adds denormal range fix-ups we do not need)
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 // [64 rows][64 x 16-bit] tile, 16-byte chunks XOR-swizzled by (row & 7): conflict-free for cp.async and ldmatrix
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const uint16_t* __restri
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     const float LOG2E = 1.4426950408889634f;
     const int qrow0 = qt * TQ + warp * 16 + g;     // rows qrow0 and qrow0 + 8
+    const bool warp_active = (qt * TQ + warp * 16) < T;   // warp-uniform: T = 257 leaves 3 of 4 warps idle in the last query tile
 
     for (int kb = 0; kb < nkb; kb++) {
         const int buf = kb & 1;
@@ -106,6 +115,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const uint16_t* __restri
             for (int ks = 0; ks < 4; ks++)
                 ldsm_x4(q_s + tile_off(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
         }
+        if (warp_active) {
+        // keys actually present in this block (T = 257: the 5th block holds ONE key) -> only the n-tile pairs / 16-key steps that
+        // contain valid keys are computed; everything beyond is masked to -inf / multiplies p = 0 anyway
+        const int kvalid = min(TK, T - kb * TK);
+        const int np_lim = (kvalid + 15) >> 4;            // pairs of 8-key n-tiles == 16-key PV steps
         // ---- S = Q K^T (16 x 64 per warp)
         float s[8][4];
         #pragma unroll
@@ -114,6 +128,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const uint16_t* __restri
         for (int ks = 0; ks < 4; ks++) {
             #pragma unroll
             for (int np = 0; np < 4; np++) {
+                if (np >= np_lim) break;
                 uint32_t b0, b1, b2, b3;
                 const int id = lane >> 3, rr = lane & 7;
                 ldsm_x4(k_s[buf] + tile_off((np * 2 + (id >> 1)) * 8 + rr, ks * 2 + (id & 1)), b0, b1, b2, b3);
@@ -123,13 +138,16 @@ __global__ void __launch_bounds__(128) attention_kernel(const uint16_t* __restri
         }
         // ---- mask + online softmax (rows g and g+8 of this warp's 16)
         const int key0 = kb * TK;
-        #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
+        // masking is only needed in the last (ragged) key block and, for the causal text tower, on the diagonal block
+        if (key0 + TK > T || (causal && key0 + TK - 1 > qt * TQ + warp * 16)) {
             #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int key = key0 + nt * 8 + 2 * t4 + (e & 1);
-                const int qr = qrow0 + ((e >> 1) ? 8 : 0);
-                if (key >= T || (causal && key > qr)) s[nt][e] = -INFINITY;
+            for (int nt = 0; nt < 8; nt++) {
+                #pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const int key = key0 + nt * 8 + 2 * t4 + (e & 1);
+                    const int qr = qrow0 + ((e >> 1) ? 8 : 0);
+                    if (key >= T || (causal && key > qr)) s[nt][e] = -INFINITY;
+                }
             }
         }
         #pragma unroll
@@ -141,12 +159,12 @@ __global__ void __launch_bounds__(128) attention_kernel(const uint16_t* __restri
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             const float m_new = fmaxf(m_run[r], mx);
             // rows past T (zero Q) and every real row see at least one unmasked key per visited block, so m_new is finite
-            const float alpha = exp2f((m_run[r] - m_new) * LOG2E);
+            const float alpha = ex2((m_run[r] - m_new) * LOG2E);
             const float mb = m_new * LOG2E;
             float rs = 0.f;
             #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
-                const float p0 = exp2f(s[nt][2 * r] * LOG2E - mb), p1 = exp2f(s[nt][2 * r + 1] * LOG2E - mb);
+                const float p0 = ex2(s[nt][2 * r] * LOG2E - mb), p1 = ex2(s[nt][2 * r + 1] * LOG2E - mb);
                 s[nt][2 * r] = p0; s[nt][2 * r + 1] = p1;
                 rs += p0 + p1;
             }
@@ -158,6 +176,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const uint16_t* __restri
         // ---- O += P V
         #pragma unroll
         for (int ks = 0; ks < 4; ks++) {
+            if (ks >= np_lim) break;
             uint32_t pa[4];
             pa[0] = pack2<BF>(s[2 * ks][0], s[2 * ks][1]);
             pa[1] = pack2<BF>(s[2 * ks][2], s[2 * ks][3]);
@@ -172,6 +191,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const uint16_t* __restri
                 mma16816<BF>(o[2 * np + 1], pa, v2, v3);
             }
         }
+        }   // warp_active
         __syncthreads();
     }
 

@@ -217,6 +217,7 @@ struct P2<false> {   // fp16: 0x6400 = 1024.0, one ulp = 1
     CB_DEVINL static uint32_t splat_from_f16bits(uint16_t h) { return (uint32_t)h | ((uint32_t)h << 16); }
     CB_DEVINL static uint32_t splat_const(float v) { return splat_from_f16bits(__half_as_ushort(__float2half_rn(v))); }
     CB_DEVINL static uint16_t from_float(float v) { return __half_as_ushort(__float2half_rn(v)); }
+    CB_DEVINL static float to_float(uint16_t b) { return __half2float(__ushort_as_half(b)); }
 };
 template <>
 struct P2<true> {    // bf16: 0x4300 = 128.0, one ulp = 1
@@ -230,6 +231,7 @@ struct P2<true> {    // bf16: 0x4300 = 128.0, one ulp = 1
     }
     CB_DEVINL static uint32_t splat_const(float v) { const uint16_t b = __bfloat16_as_ushort(__float2bfloat16_rn(v)); return (uint32_t)b | ((uint32_t)b << 16); }
     CB_DEVINL static uint16_t from_float(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+    CB_DEVINL static float to_float(uint16_t b) { return __uint_as_float((uint32_t)b << 16); }
 };
 
 CB_DEVINL float gelu_tanh(float x) {   // reference formula: ggml/src/ggml.c:3756-3758

@@ -37,26 +37,59 @@ CB_DEVINL void row_stats(Load load, int h4, int lane, float inv_h, float eps, fl
     rstd = rsqrtf(warp_sum(q) * inv_h + eps);
 }
 
-template <bool BF>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, size_t in_stride, int rows, int h, float eps,
+// K2 LayerNorm (+ fused residual add).  One warp per row, the row lives in registers (h <= 2048): one read of x, optional
+// read of the 16-bit branch output `delta` that the preceding GEMM wrote (x_new = x + delta is written back in fp32 -- this
+// replaces a read-modify-write epilogue in the GEMM, which was latency-bound), mean and CENTRED variance as the reference
+// computes them (ggml.c:10822-10840), affine, 16-bit store.
+template <bool BF, bool DELTA>
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, size_t in_stride, int rows, int h, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        uint16_t* __restrict__ y) {
+                                                        const uint16_t* __restrict__ delta, uint16_t* __restrict__ y) {
+    constexpr int MAXV = 16;                      // float4 per lane -> h <= 2048
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float* xr = x + (size_t)row * in_stride;
+    float* xr = x + (size_t)row * in_stride;
+    const uint16_t* dr = DELTA ? delta + (size_t)row * in_stride : nullptr;
     const int h4 = h >> 2;
-    auto load = [&](int i) { return ld4(xr + 4 * i); };
-    float mean, rstd;
-    row_stats(load, h4, lane, 1.0f / (float)h, eps, mean, rstd);
+    float4 v[MAXV];
+    float s = 0.f;
+    #pragma unroll
+    for (int j = 0; j < MAXV; j++) {
+        const int i = lane + 32 * j;
+        if (i < h4) {
+            v[j] = ld4(xr + 4 * i);
+            if constexpr (DELTA) {
+                const uint2 d = *reinterpret_cast<const uint2*>(dr + 4 * i);
+                v[j].x += P2<BF>::to_float((uint16_t)(d.x & 0xffffu)); v[j].y += P2<BF>::to_float((uint16_t)(d.x >> 16));
+                v[j].z += P2<BF>::to_float((uint16_t)(d.y & 0xffffu)); v[j].w += P2<BF>::to_float((uint16_t)(d.y >> 16));
+                *reinterpret_cast<float4*>(xr + 4 * i) = v[j];
+            }
+            s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        }
+    }
+    const float mean = warp_sum(s) / (float)h;
+    float q = 0.f;
+    #pragma unroll
+    for (int j = 0; j < MAXV; j++) {
+        if (lane + 32 * j < h4) {
+            const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)h + eps);
     uint16_t* yr = y + (size_t)row * h;
-    for (int i = lane; i < h4; i += 32) {
-        const float4 v = load(i), g = ld4(gamma + 4 * i), b = ld4(beta + 4 * i);
-        const float o0 = (v.x - mean) * rstd * g.x + b.x, o1 = (v.y - mean) * rstd * g.y + b.y;
-        const float o2 = (v.z - mean) * rstd * g.z + b.z, o3 = (v.w - mean) * rstd * g.w + b.w;
-        uint2 pk;
-        pk.x = (uint32_t)P2<BF>::from_float(o0) | ((uint32_t)P2<BF>::from_float(o1) << 16);
-        pk.y = (uint32_t)P2<BF>::from_float(o2) | ((uint32_t)P2<BF>::from_float(o3) << 16);
-        *reinterpret_cast<uint2*>(yr + 4 * i) = pk;
+    #pragma unroll
+    for (int j = 0; j < MAXV; j++) {
+        const int i = lane + 32 * j;
+        if (i < h4) {
+            const float4 g = ld4(gamma + 4 * i), b = ld4(beta + 4 * i);
+            const float o0 = (v[j].x - mean) * rstd * g.x + b.x, o1 = (v[j].y - mean) * rstd * g.y + b.y;
+            const float o2 = (v[j].z - mean) * rstd * g.z + b.z, o3 = (v[j].w - mean) * rstd * g.w + b.w;
+            uint2 pk;
+            pk.x = (uint32_t)P2<BF>::from_float(o0) | ((uint32_t)P2<BF>::from_float(o1) << 16);
+            pk.y = (uint32_t)P2<BF>::from_float(o2) | ((uint32_t)P2<BF>::from_float(o3) << 16);
+            *reinterpret_cast<uint2*>(yr + 4 * i) = pk;
+        }
     }
 }
 
@@ -126,12 +159,23 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ v
     for (int i = lane; i < d; i += 32) out[(size_t)row * d + i] = vr[i] * inv;
 }
 
+template <bool BF>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int h,
-                                                          int stride_rows, const int32_t* __restrict__ offs) {
+                                                          int stride_rows, const int32_t* __restrict__ offs,
+                                                          const uint16_t* __restrict__ delta) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
-    const float* s = src + ((size_t)row * stride_rows + (offs ? offs[row] : 0)) * h;
-    for (int i = lane; i < (h >> 2); i += 32) *reinterpret_cast<float4*>(dst + (size_t)row * h + 4 * i) = ld4(s + 4 * i);
+    const size_t r = (size_t)row * stride_rows + (offs ? offs[row] : 0);
+    const float* s = src + r * h;
+    for (int i = lane; i < (h >> 2); i += 32) {
+        float4 v = ld4(s + 4 * i);
+        if (delta) {
+            const uint2 d = *reinterpret_cast<const uint2*>(delta + r * h + 4 * i);
+            v.x += P2<BF>::to_float((uint16_t)(d.x & 0xffffu)); v.y += P2<BF>::to_float((uint16_t)(d.x >> 16));
+            v.z += P2<BF>::to_float((uint16_t)(d.y & 0xffffu)); v.w += P2<BF>::to_float((uint16_t)(d.y >> 16));
+        }
+        *reinterpret_cast<float4*>(dst + (size_t)row * h + 4 * i) = v;
+    }
 }
 
 // logits[i, j] = <img_i, txt_j>; small (n_img x n_txt x d), one warp per output element group
@@ -210,11 +254,16 @@ inline int rows_grid(int rows, int warps_per_block) { return (rows + warps_per_b
 
 }  // namespace
 
-void launch_layernorm(const float* x, size_t in_stride, int rows, int h, float eps, const float* gamma, const float* beta,
-                      void* y16, int out_bf16, cudaStream_t st) {
+void launch_layernorm(float* x, size_t in_stride, int rows, int h, float eps, const float* gamma, const float* beta,
+                      const void* delta16, void* y16, int bf16, cudaStream_t st) {
     if (rows <= 0) return;
-    if (out_bf16) layernorm_kernel<true><<<rows_grid(rows, 8), 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, (uint16_t*)y16);
-    else layernorm_kernel<false><<<rows_grid(rows, 8), 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, (uint16_t*)y16);
+    const int grid = rows_grid(rows, 8);
+    const uint16_t* d = (const uint16_t*)delta16;
+    uint16_t* y = (uint16_t*)y16;
+    if (bf16) { if (d) layernorm_kernel<true, true><<<grid, 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, d, y);
+                else layernorm_kernel<true, false><<<grid, 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, d, y); }
+    else      { if (d) layernorm_kernel<false, true><<<grid, 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, d, y);
+                else layernorm_kernel<false, false><<<grid, 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, d, y); }
 }
 
 void launch_im2col(const float* pixels, int B, int S, int P, int kpad, void* patches16, cudaStream_t st) {
@@ -242,9 +291,11 @@ void launch_l2norm(const float* v, float* out, int rows, int d, int normalize, c
     l2norm_kernel<<<rows_grid(rows, 8), 256, 0, st>>>(v, out, rows, d, normalize);
 }
 
-void launch_gather_rows(const float* src, float* dst, int rows, int h, int stride_rows, const int32_t* offs, cudaStream_t st) {
+void launch_gather_rows(const float* src, float* dst, int rows, int h, int stride_rows, const int32_t* offs, const void* delta16,
+                        int bf16, cudaStream_t st) {
     if (rows <= 0) return;
-    gather_rows_kernel<<<rows_grid(rows, 8), 256, 0, st>>>(src, dst, rows, h, stride_rows, offs);
+    if (bf16) gather_rows_kernel<true><<<rows_grid(rows, 8), 256, 0, st>>>(src, dst, rows, h, stride_rows, offs, (const uint16_t*)delta16);
+    else gather_rows_kernel<false><<<rows_grid(rows, 8), 256, 0, st>>>(src, dst, rows, h, stride_rows, offs, (const uint16_t*)delta16);
 }
 
 void launch_logits(const float* img, const float* txt, float* logits, int n_img, int n_txt, int d, cudaStream_t st) {

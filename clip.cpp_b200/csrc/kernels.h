@@ -7,8 +7,9 @@ namespace cb {
 
 // K2 LayerNorm: y16[r, :] = ((x[r*in_stride ...] - mean) * rstd) * gamma + beta   (reference: ggml.c:10796-10845,
 // affine clip.cpp:1071-1074).  x fp32, row r starts at x + r*in_stride.  One warp per row.
-void launch_layernorm(const float* x, size_t in_stride, int rows, int h, float eps, const float* gamma, const float* beta,
-                      void* y16, int out_bf16, cudaStream_t st);
+// If delta16 != NULL the kernel first applies the pending residual branch: x[r,:] += delta16[r,:] (written back in fp32).
+void launch_layernorm(float* x, size_t in_stride, int rows, int h, float eps, const float* gamma, const float* beta,
+                      const void* delta16, void* y16, int bf16, cudaStream_t st);
 
 // K0a im2col for the stride-P patch conv: pixels NHWC f32 [B,S,S,3] -> fp16 [B*Np, kpad], k = c*P*P + ky*P + kx,
 // zero padded to kpad (reference conv_2d im2col, ggml.c:13595-13631; pixel -> fp16 rounding ggml.c:13623).
@@ -31,7 +32,8 @@ void launch_attention(const void* qkv16, void* out16, int nseq, int T, int H, in
 void launch_l2norm(const float* v, float* out, int rows, int d, int normalize, cudaStream_t st);
 
 // gather rows: dst[r,:] = src[idx(r),:] where idx(r) = r*stride_rows + offs[r] (offs may be null -> 0)
-void launch_gather_rows(const float* src, float* dst, int rows, int h, int stride_rows, const int32_t* offs, cudaStream_t st);
+void launch_gather_rows(const float* src, float* dst, int rows, int h, int stride_rows, const int32_t* offs, const void* delta16,
+                        int bf16, cudaStream_t st);   // dst = src[idx] (+ delta16[idx])
 
 // zero-shot scoring (clip.cpp:1591-1622 semantics per row): p = (exp(s) + 1e-9) / sum
 void launch_logits(const float* img, const float* txt, float* logits, int n_img, int n_txt, int d, cudaStream_t st);

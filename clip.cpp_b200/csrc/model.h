@@ -31,6 +31,7 @@ struct Workspace {
     int cap_items = 0, T = 0, cap_rows = 0;
     float* x = nullptr;          // residual stream fp32 [rows, h]
     uint16_t* a = nullptr;       // LN output / attention output 16-bit [rows, h]
+    uint16_t* d = nullptr;       // pending residual branch (out-proj / FC2 output) 16-bit [rows, h]
     uint16_t* qkv = nullptr;     // [rows, 3h]
     uint16_t* g = nullptr;       // [rows, ff]
     uint16_t* sel16 = nullptr;   // CLS / EOT rows after post-LN [items, h]
