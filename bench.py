@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-text", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -297,6 +298,26 @@ def main():
 
     value = B * world / (ms_step / 1e3)
     e2e = B * world / (ms_e2e / 1e3)
+
+    # ---- secondary line: text-embeddings/sec, 2048 x 77-token sequences per GPU (BASELINE.json configs[3] shape) -------------
+    text = None
+    if lib.lib.clip_get_text_hparams(ctx).contents.n_layer > 0 and not args.no_text:
+        TB, TL = 2048, 77
+        ids = sg.synth_tokens(TB, TL, 2000 + rank)
+        d_ids = L.clip_b200_device_malloc(ctx, ids.nbytes)
+        d_tout = L.clip_b200_device_malloc(ctx, TB * d * 4)
+        assert L.clip_b200_memcpy_h2d(ctx, d_ids, ids.ctypes.data, ids.nbytes)
+
+        def step_text():
+            assert L.clip_b200_text_encode_device(ctx, d_ids, None, TB, TL, d_tout, True), lib.last_error()
+
+        for _ in range(3):
+            step_text()
+        ms_text, _ = timed(step_text, max(2, args.steps))
+        for k in range(4):
+            L.clip_b200_kernel_ms(ctx, k, None)
+        text = {"metric": "text-embeddings/sec", "value": TB * world / (ms_text / 1e3), "unit": "seq/s", "ms_per_step": ms_text,
+                "batch_per_gpu": TB, "tokens": TL, "tower": "ViT-L/14 text tower (h=768, 12 layers) q4_0"}
     if rank == 0:
         peak, peak_src = peaks()
         gemm_ms = kinds["gemm"]["ms_per_step"]
@@ -316,7 +337,7 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cpu, _ = cpu_reference_sample(model, 8, min(os.cpu_count() or 8, 32))
+                cpu, _ = cpu_reference_sample(model, 8, pick_threads(model))
             except Exception as e:           # the baseline leg must never take the GPU number down with it
                 cpu = {"value": None, "unit": "img/s", "cores": None, "kind": "unavailable", "sample": str(e)[:200]}
         out = {
@@ -331,7 +352,7 @@ def main():
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": None, "kernel": "gemm_dq_kernel (all fused-dequant GEMMs of the step)",
                          "flops_per_step": F_GEMM * B, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src},
-            "kernel_time_ms_per_step": kinds, "wall_ms_per_step": ms_wall, "parity": parity, "cpu_baseline": cpu,
+            "kernel_time_ms_per_step": kinds, "wall_ms_per_step": ms_wall, "parity": parity, "cpu_baseline": cpu, "text": text,
         }
         print(json.dumps(out), flush=True)
     lib.free(ctx)

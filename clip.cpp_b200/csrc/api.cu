@@ -230,7 +230,9 @@ bool ensure_ws(clip_ctx* c, Tower& tw, int items, int T, bool vision) {
         !dev_alloc(c, &w.g, rows * tw.ff) || !dev_alloc(c, &w.sel16, (size_t)items * h) || !dev_alloc(c, &w.sel32, (size_t)items * h) ||
         !dev_alloc(c, &w.proj32, (size_t)items * tw.proj)) return false;
     bool ok = make_tma_2d_16bit(&w.map_a, w.a, rows, h, h, GEMM_BN) && make_tma_2d_16bit(&w.map_g, w.g, rows, tw.ff, tw.ff, GEMM_BN) &&
-              make_tma_2d_16bit(&w.map_sel, w.sel16, items, h, h, GEMM_BN);
+              make_tma_2d_16bit(&w.map_sel, w.sel16, items, h, h, GEMM_BN) &&
+              make_tma_2d_16bit(&w.map_q128, w.qkv, rows, 3 * h, 3 * h, 128) && make_tma_2d_16bit(&w.map_kv256, w.qkv, rows, 3 * h, 3 * h, 256) &&
+              make_tma_2d_16bit(&w.map_kv16, w.qkv, rows, 3 * h, 3 * h, 16);
     if (vision) {
         const size_t per = (size_t)tw.image_size * tw.image_size * 3;
         if (!dev_alloc(c, &w.pixels[0], items * per) || !dev_alloc(c, &w.pixels[1], items * per) ||
@@ -271,7 +273,13 @@ bool run_blocks(clip_ctx* c, Tower& tw, int nseq, int T, bool causal) {
     for (auto& l : tw.L) {
         { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln1_g, l.ln1_b, pending ? w.d : nullptr, w.a, bf, c->stream); }
         if (!run_linear(c, l.qkv, &w.map_a, w.a, bf, M, w.qkv, 3 * h, EPI_STORE16, bf, h, qscale)) return false;
-        { Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, c->stream); }
+        if (c->attn_tc && attention_tc_supported(T)) {
+            const int q_done = attention_tc_tiles(T) * 128;
+            { Scope s(c, K_ATTN); CK(launch_attention_tc(&w.map_q128, &w.map_kv256, &w.map_kv16, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, c->num_sms, c->stream)); }
+            if (q_done < T) { Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, q_done, c->stream); }
+        } else {
+            Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, 0, c->stream);
+        }
         if (!run_linear(c, l.out, &w.map_a, w.a, bf, M, w.d, h, EPI_STORE16, bf)) return false;
         { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln2_g, l.ln2_b, w.d, w.a, bf, c->stream); }
         if (!run_linear(c, l.fc1, &w.map_a, w.a, bf, M, w.g, tw.ff, c->use_gelu ? EPI_GELU16 : EPI_QGELU16, bf)) return false;
@@ -396,7 +404,8 @@ struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
         }
         cudaEventCreate(&c->ev_t0);
         cudaEventCreate(&c->ev_t1);
-        if (gemm_init() != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem) failed"); return nullptr; }
+        if (gemm_init() != cudaSuccess || attention_tc_init() != cudaSuccess) { set_err("cudaFuncSetAttribute(max dynamic smem) failed"); return nullptr; }
+        if (const char* at = getenv("CLIP_B200_ATTN")) c->attn_tc = strcmp(at, "legacy") != 0;
 
         if (!kv_bool(g, "clip.has_text_encoder", c->has_text) || !kv_bool(g, "clip.has_vision_encoder", c->has_vision) ||
             !kv_bool(g, "clip.use_gelu", c->use_gelu)) return nullptr;

@@ -45,6 +45,7 @@ struct Workspace {
     int32_t* ids = nullptr;
     int32_t* last = nullptr;     // index of the EOT row per sequence (len - 1)
     TmaMap map_a, map_g, map_patches, map_sel;
+    TmaMap map_q128, map_kv256, map_kv16;   // views of qkv for the tcgen05 attention kernel
 };
 
 struct Tower {
@@ -83,7 +84,7 @@ struct clip_ctx {
     std::vector<void*> allocs;   // every device allocation, freed in clip_free
     float* d_out = nullptr;      // result staging [n, d]
     size_t d_out_cap = 0;
-    bool debug_naive = false, profile = false;
+    bool debug_naive = false, profile = false, attn_tc = true;
     uint64_t launches = 0;
     float last_ms = 0.f;
     std::vector<cb::ProfEvent> prof;
