@@ -6,10 +6,10 @@
 //               (row stride 3*hidden), 128B swizzle, 2-stage ring -> the next item's loads overlap this item's math
 //   warp 1      one elected thread: S[128 x nk] = Q.K^T (SS form, K=64 -> 4 UMMA k-steps; N = 256 (+16) columns), then
 //               O[128 x 64] = P.V (TS form: A = P from TMEM, B = V taken MN-major from the same [key][dh] tile, K = nk)
-//   warps 4-7   softmax in the TMEM lane == query-row mapping (no cross-thread reduction at all): pass 1 row max over
-//               tcgen05.ld chunks, pass 2 p = 2^((s-m)*log2e) -> bf16/fp16 pairs written back IN PLACE over the consumed half
-//               of S (tcgen05.st), row sum kept in fp32; after the PV commit: O / l -> 128-byte row stores
-//   warp 2      TMEM alloc (S/P: columns [0,272), O: [272,336))
+//   warps 4-11  softmax in the TMEM lane == query-row mapping (two warps per lane quarter split the key chunks): pass 1 row max over
+//               tcgen05.ld chunks, pass 2 p = 2^((s-m)*log2e) -> bf16/fp16 pairs written to the P columns
+//               (tcgen05.st), row sum kept in fp32; after the PV commit: O / l -> 128-byte row stores
+//   warp 2      TMEM alloc (S: columns [0,272), P: [272,408), O: [408,472))
 // HBM traffic: Q, K, V read once per (sequence, head) (K/V re-reads of the second query tile hit L2), O written once.
 // Limits: head_dim 64, T <= 272 keys; query rows beyond the last full 128-tile (e.g. row 256 of ViT-L/14's 257) are left
 // to the warp-level kernel in attention.cu, launched with a query offset.
@@ -28,8 +28,8 @@ constexpr uint32_t Q_BYTES = AQ * 128, KV_BYTES = AKMAX * 128;
 constexpr uint32_t STAGE = Q_BYTES + 2 * KV_BYTES;     // 86016
 constexpr int NS = 2;
 constexpr uint32_t BAR_OFF = NS * STAGE;
-constexpr uint32_t ATT_SMEM = BAR_OFF + 256 + 1024;
-constexpr uint32_t O_COL = 272;
+constexpr uint32_t ATT_SMEM = BAR_OFF + 128 + 2048 /*row max / row sum exchange*/ + 1024;
+constexpr uint32_t P_COL = 272, O_COL = 408;   // TMEM columns: S [0,272)  P (16-bit pairs) [272,408)  O [408,472)
 static_assert(STAGE % 1024 == 0, "stage alignment");
 
 struct AParams {
@@ -77,7 +77,7 @@ CB_DEVINL uint64_t umma_desc_mn128(uint32_t smem_addr) {
 }
 
 template <bool BF>
-__global__ void __launch_bounds__(256, 1) attention_tc_kernel(const __grid_constant__ AParams p) {
+__global__ void __launch_bounds__(384, 1) attention_tc_kernel(const __grid_constant__ AParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256, 1) attention_tc_kernel(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; i++) { mbar_init(kv_full + 8 * i, 1); mbar_init(kv_empty + 8 * i, 1); }
-        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_empty, 4);
+        mbar_init(s_full, 1); mbar_init(p_full, 8); mbar_init(o_full, 1); mbar_init(o_empty, 8);
         mbar_fence_init();
         tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_kv256); tma_prefetch_desc(&p.tm_kv16);
     }
@@ -151,68 +151,92 @@ __global__ void __launch_bounds__(256, 1) attention_tc_kernel(const __grid_const
             tc_fence_after();
             const uint64_t dv = umma_desc_mn128(qa + Q_BYTES + KV_BYTES);
             if (elect_one()) {
-                umma_f16_ts_init(tmem_base + O_COL, tmem_base, dv, id_pv);
+                umma_f16_ts_init(tmem_base + O_COL, tmem_base + P_COL, dv, id_pv);
                 for (int ks = 1; ks < npv; ks++)       // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2048 B) of V
-                    umma_f16_ts_acc(tmem_base + O_COL, tmem_base + 8 * ks, dv + (uint64_t)ks * (2048 >> 4), id_pv);
+                    umma_f16_ts_acc(tmem_base + O_COL, tmem_base + P_COL + 8 * ks, dv + (uint64_t)ks * (2048 >> 4), id_pv);
                 umma_commit(o_full);
                 umma_commit(kv_empty + 8 * s);
             }
             __syncwarp();
         }
     } else if (warp >= 4) {
-        const int r = (warp & 3) * 32 + lane;
+        // ------------------------------------------------------------------ softmax + epilogue: 8 warps, two per TMEM lane quarter.
+        // Warp pair (w, w+4) shares the 32 query rows of its quarter and splits the key chunks; row max and row sum are
+        // exchanged through shared memory (one named barrier per item), the O columns are split 32 / 32 for the store.
+        const int r = (warp & 3) * 32 + lane, half = (warp - 4) >> 2;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+        float* xmax = reinterpret_cast<float*>(smem + BAR_OFF + 128);         // [2][128]
+        float* xsum = xmax + 256;                                             // [2][128]
         const float LOG2E = 1.4426950408889634f;
         const int nch = (p.nk16 + 31) >> 5;
+        const int c_lo = half ? (nch + 1) / 2 : 0, c_hi = half ? nch : (nch + 1) / 2;
         int j = 0;
         for (int it = blockIdx.x; it < total; it += gridDim.x, j++) {
             const int qt = it % p.ntile, head = (it / p.ntile) % p.H, seq = it / (p.ntile * p.H);
             const uint32_t jp = j & 1;
             const int qrow = qt * AQ + r;
             const int klim = p.causal ? min(p.T, qrow + 1) : p.T;      // keys [0, klim) are visible to this row
+            const int klim_min = __shfl_sync(0xffffffffu, klim, 0);    // lane 0 holds the smallest row of the warp
             mbar_wait(s_full, jp);
             tc_fence_after();
-            // ---- pass 1: row max
+            // ---- pass 1: row max over this warp's chunks
             float m = -INFINITY;
-            for (int c = 0; c < nch; c++) {
+            for (int c = c_lo; c < c_hi; c++) {
                 uint32_t v[32];
                 tmem_ld_32x32(lane_addr + c * 32, v);
                 tmem_ld_wait();
-                #pragma unroll
-                for (int i = 0; i < 32; i++)
-                    if (c * 32 + i < klim) m = fmaxf(m, __uint_as_float(v[i]));
+                if (c * 32 + 32 <= klim_min) {                         // warp-uniform: every key of the chunk is visible
+                    #pragma unroll
+                    for (int i = 0; i < 32; i++) m = fmaxf(m, __uint_as_float(v[i]));
+                } else {
+                    #pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if (c * 32 + i < klim) m = fmaxf(m, __uint_as_float(v[i]));
+                }
             }
+            xmax[half * 128 + r] = m;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            m = fmaxf(m, xmax[(half ^ 1) * 128 + r]);
             if (m == -INFINITY) m = 0.f;                               // padded query rows past T
             const float mb = m * LOG2E;
-            // ---- pass 2: p = 2^(s*log2e - m*log2e), packed 16-bit pairs overwrite the already-consumed low half of S
+            // ---- pass 2: p = 2^(s*log2e - m*log2e) as packed 16-bit pairs into the P columns
             float l = 0.f;
-            for (int c = 0; c < nch; c++) {
+            for (int c = c_lo; c < c_hi; c++) {
                 uint32_t v[32], pk[16];
                 tmem_ld_32x32(lane_addr + c * 32, v);
                 tmem_ld_wait();
-                #pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const int k0 = c * 32 + 2 * i;
-                    const float p0 = (k0 < klim) ? ex2f(__uint_as_float(v[2 * i]) * LOG2E - mb) : 0.f;
-                    const float p1 = (k0 + 1 < klim) ? ex2f(__uint_as_float(v[2 * i + 1]) * LOG2E - mb) : 0.f;
-                    l += p0 + p1;
-                    pk[i] = pack2<BF>(p0, p1);
+                if (c * 32 + 32 <= klim_min) {
+                    #pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float p0 = ex2f(__uint_as_float(v[2 * i]) * LOG2E - mb), p1 = ex2f(__uint_as_float(v[2 * i + 1]) * LOG2E - mb);
+                        l += p0 + p1;
+                        pk[i] = pack2<BF>(p0, p1);
+                    }
+                } else {
+                    #pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int k0 = c * 32 + 2 * i;
+                        const float p0 = (k0 < klim) ? ex2f(__uint_as_float(v[2 * i]) * LOG2E - mb) : 0.f;
+                        const float p1 = (k0 + 1 < klim) ? ex2f(__uint_as_float(v[2 * i + 1]) * LOG2E - mb) : 0.f;
+                        l += p0 + p1;
+                        pk[i] = pack2<BF>(p0, p1);
+                    }
                 }
-                tmem_st_32x16(lane_addr + c * 16, pk);
+                tmem_st_32x16(lane_addr + P_COL + c * 16, pk);     // P has its own columns: the two warps of a quarter never alias
             }
+            xsum[half * 128 + r] = l;
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
-            // ---- O / l -> global
+            // ---- O / l -> global (this warp stores 32 of the 64 head-dim columns)
             mbar_wait(o_full, jp);
             tc_fence_after();
-            const float inv = 1.0f / l;
-            uint16_t* orow = p.out + ((size_t)seq * p.T + qrow) * hid + head * DH;
-            #pragma unroll
-            for (int h2 = 0; h2 < 2; h2++) {
+            const float inv = 1.0f / (l + xsum[(half ^ 1) * 128 + r]);
+            uint16_t* orow = p.out + ((size_t)seq * p.T + qrow) * hid + head * DH + half * 32;
+            {
                 uint32_t v[32];
-                tmem_ld_32x32(lane_addr + O_COL + h2 * 32, v);
+                tmem_ld_32x32(lane_addr + O_COL + half * 32, v);
                 tmem_ld_wait();
                 if (qrow < p.T) {
                     #pragma unroll
@@ -222,7 +246,7 @@ __global__ void __launch_bounds__(256, 1) attention_tc_kernel(const __grid_const
                         q4.y = pack2<BF>(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv);
                         q4.z = pack2<BF>(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv);
                         q4.w = pack2<BF>(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv);
-                        *reinterpret_cast<uint4*>(orow + h2 * 32 + 8 * i) = q4;
+                        *reinterpret_cast<uint4*>(orow + 8 * i) = q4;
                     }
                 }
             }
@@ -265,8 +289,8 @@ cudaError_t launch_attention_tc(const TmaMap* map_q, const TmaMap* map_kv256, co
     p.nk16 = ((T + 15) / 16) * 16;
     const int total = nseq * H * p.ntile;
     const int grid = total < num_sms ? total : num_sms;
-    if (bf16) attention_tc_kernel<true><<<grid, 256, ATT_SMEM, st>>>(p);
-    else attention_tc_kernel<false><<<grid, 256, ATT_SMEM, st>>>(p);
+    if (bf16) attention_tc_kernel<true><<<grid, 384, ATT_SMEM, st>>>(p);
+    else attention_tc_kernel<false><<<grid, 384, ATT_SMEM, st>>>(p);
     return cudaGetLastError();
 }
 
