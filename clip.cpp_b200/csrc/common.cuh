@@ -79,6 +79,40 @@ CB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // --------------------------------------------------------------------------------------------------
+// CTA pairs (cluster of 2): rank, remote (cluster-scope) barrier arrive, cluster barrier
+// --------------------------------------------------------------------------------------------------
+CB_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+CB_DEVINL uint32_t mapa_rank0(uint32_t addr) {   // shared::cluster address of `addr` inside CTA rank 0 of this cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+    return r;
+}
+CB_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+CB_DEVINL bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+CB_DEVINL void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > CB_WAIT_TIMEOUT_CYCLES) __trap();
+    }
+}
+CB_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// --------------------------------------------------------------------------------------------------
 // proxies / fences
 // --------------------------------------------------------------------------------------------------
 // generic-proxy smem writes (st.shared) -> visible to the async proxy (UMMA operand reads, TMA stores)
@@ -98,6 +132,14 @@ CB_DEVINL void tma_load_2d(uint32_t dst_smem, const void* tmap, int c0, int c1, 
         "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// CTA-pair variant: the data lands in THIS CTA's shared memory, the transaction bytes are credited to the mbarrier of the
+// pair's leader CTA (bar_cluster = mapa_rank0(local barrier address))
+CB_DEVINL void tma_load_2d_2sm(uint32_t dst_smem, const void* tmap, int c0, int c1, uint32_t bar_cluster) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst_smem),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
 CB_DEVINL void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
@@ -110,6 +152,13 @@ CB_DEVINL void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, 
 CB_DEVINL void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+CB_DEVINL void tmem_alloc_2sm(uint32_t dst_smem, uint32_t ncols) {   // executed by the same warp id in BOTH CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+CB_DEVINL void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 CB_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
@@ -196,6 +245,29 @@ CB_DEVINL void umma_f16_ts_init(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
         "r"(tmem_a), "l"(desc_b), "r"(idesc)
         : "memory");
+}
+// CTA-pair (cta_group::2) forms: ONE instruction from the leader drives both SMs' tensor cores (M = 256: each CTA supplies its
+// 128 A rows from its own TMEM and half of the B rows from its own shared memory); commits are multicast to both CTAs.
+CB_DEVINL void umma_f16_ts_2sm_acc(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+CB_DEVINL void umma_f16_ts_2sm_init(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc)
+        : "memory");
+}
+CB_DEVINL void umma_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
 }
 // commit all previously issued tcgen05 async ops of this thread; arrives (count 1) on the mbarrier when they finish.
 // Implies tcgen05.fence::before_thread_sync.

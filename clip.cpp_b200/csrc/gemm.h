@@ -23,6 +23,7 @@ struct GemmArgs {
     // Y[M tokens, N features] (+)= X[M, K] . W[N, K]^T (+ bias[N]),  computed as D[feature, token] tiles
     const TmaMap* x_map = nullptr;   // activations X, 16-bit, box rows = GEMM_BN
     const TmaMap* w_map = nullptr;   // QT_F16 only: weights W [N, K] fp16, box rows = GEMM_BM
+    const TmaMap* x_half_map = nullptr;   // optional: X with box rows = GEMM_BN/2 -> enables the CTA-pair (cta_group::2) kernel when N % 256 == 0
     const uint8_t* w_packed = nullptr;   // quantized types: re-tiled blocks (wpack.h)
     int qtype = 1;                   // cb::QType of W
     bool operand_bf16 = false;       // X (and the unpacked W) are bf16 instead of fp16; must be false for QT_F16

@@ -69,6 +69,7 @@ struct Cfg {
 struct KParams {
     CUtensorMap tm_x;
     CUtensorMap tm_w;
+    CUtensorMap tm_xh;    // CTA-pair kernels: activation box of BN/2 = 96 tokens (each CTA of the pair loads half the B operand)
     const uint8_t* w_packed;
     const float* bias;
     void* out;
@@ -219,12 +220,20 @@ CB_DEVINL void epilogue_tile(const KParams& p, uint32_t acc_addr, int tok0, int 
     }
 }
 
-template <int QT, bool BF>
+// PAIR = true: two CTAs (a cluster of 2 = one TPC) work on one [256 features x 192 tokens] tile with cta_group::2 UMMAs.  Each CTA
+// unpacks ITS 128 feature rows into ITS tensor memory and TMA-loads HALF of the token tile (96 rows); the leader CTA (rank 0)
+// issues every MMA (M = 256) and multicasts the commits; the peer's TMA bytes, A-stage arrivals and accumulator releases are
+// credited to the leader's mbarriers (cluster-scope arrive / cta_group::2 TMA).  Halves the activation traffic per CTA and lifts
+// the single-CTA UMMA issue ceiling measured in profiles/r01_gemm_probe.txt.
+template <int QT, bool BF, bool PAIR>
 __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(const __grid_constant__ KParams p) {
     using C = Cfg<QT>;
     constexpr bool DQ = C::DQ;
+    static_assert(!PAIR || DQ, "pair kernels exist for the quantized (TS-form) path only");
     constexpr int SX = C::SX, SQ = DQ ? C::SQ : 1;
-    constexpr uint32_t IDESC = umma_idesc(BF, BM, BN);
+    constexpr uint32_t IDESC = umma_idesc(BF, PAIR ? 2 * BM : BM, BN);
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -241,32 +250,43 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
     if (threadIdx.x == 0) {
         for (int i = 0; i < SX; i++) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 1); }
         for (int i = 0; i < SQ; i++) { mbar_init(q_full + 8 * i, 1); mbar_init(q_empty + 8 * i, 4); }
-        for (int i = 0; i < NA; i++) { mbar_init(a_full + 8 * i, 4); mbar_init(a_empty + 8 * i, 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, N_EPI_WARPS); }
+        for (int i = 0; i < NA; i++) { mbar_init(a_full + 8 * i, PAIR ? 8 : 4); mbar_init(a_empty + 8 * i, 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, PAIR ? 2 * N_EPI_WARPS : N_EPI_WARPS); }
         mbar_fence_init();
         tma_prefetch_desc(&p.tm_x);
         if (!DQ) tma_prefetch_desc(&p.tm_w);
+        if (PAIR) tma_prefetch_desc(&p.tm_xh);
     }
-    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (warp == 2) { if constexpr (PAIR) tmem_alloc_2sm(smem_u32(tmem_slot), TMEM_COLS); else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS); }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();      // the peer's barriers must be initialised before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int n_ft = p.N / BM, n_tt = (p.M + BN - 1) / BN, n_tiles = n_ft * n_tt, nkb = p.K / BK;
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+    // work units: 1-CTA kernels walk [128 x 192] tiles with stride gridDim; pair kernels walk [256 x 192] tiles with stride gridDim/2
+    const int n_ft = p.N / (PAIR ? 2 * BM : BM), n_tt = (p.M + BN - 1) / BN, n_tiles = n_ft * n_tt, nkb = p.K / BK;
+    const int first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int my_tiles = (n_tiles - first + stride - 1) / stride;                              // tiles of this CTA (pair)
     const int total_kb = my_tiles * nkb;                                                      // k-blocks of this CTA
 
     if (warp == 0) {
         // ------------------------------------------------------------------ X producer (f16: X and W)
         uint32_t s = 0, ph = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int tile = first; tile < n_tiles; tile += stride) {
             const int ft = tile % n_ft, tt = tile / n_ft;
             for (int kb = 0; kb < nkb; kb++) {
                 mbar_wait(x_empty + 8 * s, ph ^ 1);
                 if (elect_one()) {
                     const uint32_t dst = smem_base + s * C::XS;
-                    if (p.dbg & 2) mbar_arrive(x_full + 8 * s);
+                    if constexpr (PAIR) {
+                        // both CTAs load their half of the token tile; all bytes are credited to the LEADER's x_full barrier
+                        if (p.dbg & 2) { if (leader) mbar_arrive(x_full + 8 * s); }
+                        else {
+                        if (leader) mbar_arrive_expect_tx(x_full + 8 * s, X_STAGE);
+                        tma_load_2d_2sm(dst, &p.tm_xh, kb * BK, tt * BN + (int)rank * (BN / 2), mapa_rank0(x_full + 8 * s));
+                        }
+                    } else if (p.dbg & 2) mbar_arrive(x_full + 8 * s);
                     else {
                         mbar_arrive_expect_tx(x_full + 8 * s, C::XS);
                         tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, x_full + 8 * s);
@@ -281,8 +301,8 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
         // ------------------------------------------------------------------ Q producer (packed weight blocks)
         if constexpr (DQ) {
             uint32_t s = 0, ph = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int ft = tile % n_ft;
+            for (int tile = first; tile < n_tiles; tile += stride) {
+                const int ft = PAIR ? (tile % n_ft) * 2 + (int)rank : tile % n_ft;      // 128-row feature tile this CTA unpacks
                 const uint8_t* src = p.w_packed + (size_t)ft * nkb * C::CHUNK;
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(q_empty + 8 * s, ph ^ 1);
@@ -306,7 +326,8 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
         constexpr uint64_t X_STEP = C::XS >> 4;
         uint32_t s = 0, ph = 0, sa = 0, pa = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        if (leader)
+        for (int tile = first; tile < n_tiles; tile += stride, it++) {
             const uint32_t as = it & 1, aph = (it >> 1) & 1;
             const uint32_t d_tmem = tmem_base + as * BN;
             mbar_wait(acc_empty + 8 * as, aph ^ 1);
@@ -317,7 +338,17 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 tc_fence_after();
                 const uint64_t db = dx0 + (uint64_t)s * X_STEP;
                 if (elect_one()) {
-                    if constexpr (DQ) {
+                    if constexpr (PAIR) {
+                        const uint32_t a_t = tmem_base + A_COL0 + sa * 32;
+                        if (kb == 0) umma_f16_ts_2sm_init(d_tmem, a_t, db, IDESC);
+                        else umma_f16_ts_2sm_acc(d_tmem, a_t, db, IDESC);
+                        umma_f16_ts_2sm_acc(d_tmem, a_t + 8, db + 2, IDESC);
+                        umma_f16_ts_2sm_acc(d_tmem, a_t + 16, db + 4, IDESC);
+                        umma_f16_ts_2sm_acc(d_tmem, a_t + 24, db + 6, IDESC);
+                        umma_commit_2sm(x_empty + 8 * s);
+                        umma_commit_2sm(a_empty + 8 * sa);
+                        if (kb == nkb - 1) umma_commit_2sm(acc_full + 8 * as);
+                    } else if constexpr (DQ) {
                         const uint32_t a_t = tmem_base + A_COL0 + sa * 32;      // 16 k = 8 TMEM columns per MMA step
                         if (kb == 0) umma_f16_ts_init(d_tmem, a_t, db, IDESC);
                         else umma_f16_ts_acc(d_tmem, a_t, db, IDESC);
@@ -335,7 +366,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                         umma_f16_acc(d_tmem, da + 6, db + 6, IDESC);
                         umma_commit(x_empty + 8 * s);
                     }
-                    if (kb == nkb - 1) umma_commit(acc_full + 8 * as);
+                    if (!PAIR && kb == nkb - 1) umma_commit(acc_full + 8 * as);
                 }
                 __syncwarp();
                 if (++s == SX) { s = 0; ph ^= 1; }
@@ -347,8 +378,8 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
         const int fr = (warp & 3) * 32 + lane;                     // feature row of the tile == TMEM lane
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-            const int ft = tile % n_ft, tt = tile / n_ft;
+        for (int tile = first; tile < n_tiles; tile += stride, it++) {
+            const int ft = PAIR ? (tile % n_ft) * 2 + (int)rank : tile % n_ft, tt = tile / n_ft;
             const uint32_t as = it & 1, aph = (it >> 1) & 1;
             const int n = ft * BM + fr;
             const float bias = p.bias ? p.bias[n] : 0.0f;
@@ -366,7 +397,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+            if (lane == 0) { if constexpr (PAIR) mbar_arrive_cluster(mapa_rank0(acc_empty + 8 * as)); else mbar_arrive(acc_empty + 8 * as); }
         }
     } else if (warp >= 8) {
         // ------------------------------------------------------------------ unpack groups: registers -> TMEM A stages
@@ -376,22 +407,27 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             const uint32_t a_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0;
             uint32_t qs = g, qph = 0, sa = g, pa = 0;             // ring positions of k-block i = g
             for (int i = g; i < total_kb; i += N_GROUPS) {
+                // the unpack math only needs the packed chunk: do it BEFORE waiting for the TMEM stage, so the a_empty -> a_full
+                // round trip seen by the MMA warp is just tcgen05.st + wait::st (matters most for the CTA-pair kernel)
                 mbar_wait(q_full + 8 * qs, qph);
-                mbar_wait(a_empty + 8 * sa, pa ^ 1);
-                tc_fence_after();
                 const uint32_t qa = smem_base + C::Q_OFF + qs * C::CHUNK;
+                uint32_t v[32];
                 if (!(p.dbg & 1)) {
-                    uint32_t v[32];
                     unpack_block<DQ ? QT : QT_Q4_0, BF>(qa, row, v);              // k  0..31 of this row
                     unpack_block<DQ ? QT : QT_Q4_0, BF>(qa, 128 + row, v + 16);   // k 32..63
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(q_empty + 8 * qs);
+                mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                tc_fence_after();
+                if (!(p.dbg & 1)) {
                     tmem_st_32x32(a_lane + sa * 32, v);
                     tmem_st_wait();
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(a_full + 8 * sa);
-                    mbar_arrive(q_empty + 8 * qs);
+                    if constexpr (PAIR) mbar_arrive_cluster(mapa_rank0(a_full + 8 * sa)); else mbar_arrive(a_full + 8 * sa);
                 }
                 qs += N_GROUPS; if (qs >= (uint32_t)SQ) { qs -= SQ; qph ^= 1; }
                 sa += N_GROUPS; if (sa >= (uint32_t)NA) { sa -= NA; pa ^= 1; }
@@ -401,7 +437,8 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) cluster_sync_all();      // neither CTA may exit (or free TMEM) while the pair's MMAs / multicasts are in flight
+    if (warp == 2) { if constexpr (PAIR) tmem_dealloc_2sm(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -421,12 +458,29 @@ EncodeTiledFn get_encode() {
 
 template <int QT, bool BF>
 cudaError_t launch_t(const KParams& kp, int grid, cudaStream_t st) {
-    gemm_dq_kernel<QT, BF><<<grid, QT == QT_F16 ? 256 : 512, Cfg<QT>::SMEM, st>>>(kp);
+    gemm_dq_kernel<QT, BF, false><<<grid, QT == QT_F16 ? 256 : 512, Cfg<QT>::SMEM, st>>>(kp);
     return cudaGetLastError();
 }
 template <int QT, bool BF>
+cudaError_t launch_pair_t(const KParams& kp, int grid, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = Cfg<QT>::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_dq_kernel<QT, BF, true>, kp);
+}
+template <int QT, bool BF>
 cudaError_t set_attr() {
-    return cudaFuncSetAttribute(gemm_dq_kernel<QT, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<QT>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_dq_kernel<QT, BF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<QT>::SMEM);
+    if (e != cudaSuccess) return e;
+    if constexpr (QT != QT_F16) e = cudaFuncSetAttribute(gemm_dq_kernel<QT, BF, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<QT>::SMEM);
+    return e;
 }
 
 }  // namespace
@@ -468,6 +522,8 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream, int num_sms, uin
     memcpy(&kp.tm_x, a.x_map, sizeof(CUtensorMap));
     if (a.w_map) memcpy(&kp.tm_w, a.w_map, sizeof(CUtensorMap));
     else memset(&kp.tm_w, 0, sizeof(CUtensorMap));
+    if (a.x_half_map) memcpy(&kp.tm_xh, a.x_half_map, sizeof(CUtensorMap));
+    else memset(&kp.tm_xh, 0, sizeof(CUtensorMap));
     kp.w_packed = a.w_packed;
     kp.bias = a.bias;
     kp.out = a.out;
@@ -478,6 +534,18 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream, int num_sms, uin
     const int n_tiles = (a.N / BM) * ((a.M + BN - 1) / BN);
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
     if (launches) ++*launches;
+    static const bool pair_off = getenv("CLIP_B200_GEMM_PAIR") && atoi(getenv("CLIP_B200_GEMM_PAIR")) == 0;
+    if (a.x_half_map && !pair_off && a.qtype != QT_F16 && a.N % (2 * BM) == 0) {
+        const int n_pairs_tiles = n_tiles / 2;
+        int pairs = num_sms / 2;
+        if (pairs > n_pairs_tiles) pairs = n_pairs_tiles;
+        switch (a.qtype) {
+#define CB_PCASE(QT) case QT: return a.operand_bf16 ? launch_pair_t<QT, true>(kp, 2 * pairs, stream) : launch_pair_t<QT, false>(kp, 2 * pairs, stream);
+        CB_PCASE(QT_Q4_0) CB_PCASE(QT_Q4_1) CB_PCASE(QT_Q5_0) CB_PCASE(QT_Q5_1) CB_PCASE(QT_Q8_0)
+#undef CB_PCASE
+        default: return cudaErrorInvalidValue;
+        }
+    }
     switch (a.qtype) {
     case QT_F16: return launch_t<QT_F16, false>(kp, grid, stream);
 #define CB_CASE(QT) case QT: return a.operand_bf16 ? launch_t<QT, true>(kp, grid, stream) : launch_t<QT, false>(kp, grid, stream);
