@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256, 2) attention_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();      // qkv is read (and the output written) only after the QKV GEMM grid has completed
 
     const int hid = p.H * DH, total = p.nseq * p.H * p.ntile;
     const int nmma = p.nk16 < 256 ? p.nk16 : 256;          // keys whose scores come from the tensor core
@@ -321,9 +323,9 @@ cudaError_t launch_attention_tc(const TmaMap* map_q, const TmaMap* map_kv256, co
     p.nk16 = ((T + 15) / 16) * 16;
     const int total = nseq * H * p.ntile;
     const int grid = total < 2 * num_sms ? total : 2 * num_sms;      // two CTAs per SM (256 TMEM columns, 87 KB smem each)
-    if (bf16) attention_tc_kernel<true><<<grid, 256, ATT_SMEM, st>>>(p);
-    else attention_tc_kernel<false><<<grid, 256, ATT_SMEM, st>>>(p);
-    return cudaGetLastError();
+    cudaError_t e = bf16 ? launch_pdl(attention_tc_kernel<true>, (unsigned)grid, 256u, ATT_SMEM, st, 1, p)
+                         : launch_pdl(attention_tc_kernel<false>, (unsigned)grid, 256u, ATT_SMEM, st, 1, p);
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace cb

@@ -4,6 +4,7 @@
 // no CUTLASS/CuTe dependency.  Descriptor bit layouts follow the PTX ISA "tcgen05" matrix/instruction
 // descriptor tables (cross-checked against the field tables in the vendored CuTe headers).
 #pragma once
+#include <cstdlib>
 
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -77,6 +78,14 @@ CB_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
         if (clock64() - t0 > CB_WAIT_TIMEOUT_CYCLES) __trap();
     }
 }
+
+// --------------------------------------------------------------------------------------------------
+// programmatic dependent launch: the hot kernels of a tower are launched with programmaticStreamSerialization, so the next
+// kernel's CTAs are placed (and run their barrier / TMEM / descriptor prologue) while the previous grid drains.  pdl_wait()
+// blocks until the previous grid has completed and its writes are visible: NO global memory may be touched before it.
+// --------------------------------------------------------------------------------------------------
+CB_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+CB_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // --------------------------------------------------------------------------------------------------
 // CTA pairs (cluster of 2): rank, remote (cluster-scope) barrier arrive, cluster barrier
@@ -316,6 +325,34 @@ CB_DEVINL float gelu_quick(float x) {  // x * sigmoid(1.702 x): ggml/src/ggml.c:
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
     return x * fmaf(0.5f, t, 0.5f);
+}
+
+
+// host side: launch with the PDL attribute (and optionally as clusters of `cluster_x` CTAs)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, unsigned cluster_x,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    unsigned n = 0;
+    static const bool pdl_on = !(getenv("CLIP_B200_PDL") && atoi(getenv("CLIP_B200_PDL")) == 0);   // A/B switch for measurements
+    if (pdl_on) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        n++;
+    }
+    if (cluster_x > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
+        n++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace cb

@@ -262,6 +262,8 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
     __syncthreads();
     if constexpr (PAIR) cluster_sync_all();      // the peer's barriers must be initialised before anything arrives on them remotely
     tc_fence_after();
+    pdl_trigger();      // the next kernel of the stream may start placing CTAs as ours retire ...
+    pdl_wait();         // ... and we touch global memory only after the previous grid has completed
     const uint32_t tmem_base = *tmem_slot;
 
     // work units: 1-CTA kernels walk [128 x 192] tiles with stride gridDim; pair kernels walk [256 x 192] tiles with stride gridDim/2
@@ -458,22 +460,11 @@ EncodeTiledFn get_encode() {
 
 template <int QT, bool BF>
 cudaError_t launch_t(const KParams& kp, int grid, cudaStream_t st) {
-    gemm_dq_kernel<QT, BF, false><<<grid, QT == QT_F16 ? 256 : 512, Cfg<QT>::SMEM, st>>>(kp);
-    return cudaGetLastError();
+    return launch_pdl(gemm_dq_kernel<QT, BF, false>, (unsigned)grid, QT == QT_F16 ? 256u : 512u, Cfg<QT>::SMEM, st, 1, kp);
 }
 template <int QT, bool BF>
 cudaError_t launch_pair_t(const KParams& kp, int grid, cudaStream_t st) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(512);
-    cfg.dynamicSmemBytes = Cfg<QT>::SMEM;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, gemm_dq_kernel<QT, BF, true>, kp);
+    return launch_pdl(gemm_dq_kernel<QT, BF, true>, (unsigned)grid, 512u, Cfg<QT>::SMEM, st, 2, kp);
 }
 template <int QT, bool BF>
 cudaError_t set_attr() {

@@ -41,12 +41,15 @@ CB_DEVINL void row_stats(Load load, int h4, int lane, float inv_h, float eps, fl
 // read of the 16-bit branch output `delta` that the preceding GEMM wrote (x_new = x + delta is written back in fp32 -- this
 // replaces a read-modify-write epilogue in the GEMM, which was latency-bound), mean and CENTRED variance as the reference
 // computes them (ggml.c:10822-10840), affine, 16-bit store.
-template <bool BF, bool DELTA>
+// MAXV = float4 per lane (row width h <= 128 * MAXV): specialised so a 1024-wide row costs 32 value registers, not 64 -- the kernel is
+// latency-bound on its loads (ncu: long_scoreboard), so resident warps per SM are what buys HBM bandwidth.
+template <bool BF, bool DELTA, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, size_t in_stride, int rows, int h, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         const uint16_t* __restrict__ delta, uint16_t* __restrict__ y) {
-    constexpr int MAXV = 16;                      // float4 per lane -> h <= 2048
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    pdl_trigger();
+    pdl_wait();
     if (row >= rows) return;
     float* xr = x + (size_t)row * in_stride;
     const uint16_t* dr = DELTA ? delta + (size_t)row * in_stride : nullptr;
@@ -260,10 +263,12 @@ void launch_layernorm(float* x, size_t in_stride, int rows, int h, float eps, co
     const int grid = rows_grid(rows, 8);
     const uint16_t* d = (const uint16_t*)delta16;
     uint16_t* y = (uint16_t*)y16;
-    if (bf16) { if (d) layernorm_kernel<true, true><<<grid, 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, d, y);
-                else layernorm_kernel<true, false><<<grid, 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, d, y); }
-    else      { if (d) layernorm_kernel<false, true><<<grid, 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, d, y);
-                else layernorm_kernel<false, false><<<grid, 256, 0, st>>>(x, in_stride, rows, h, eps, gamma, beta, d, y); }
+#define CB_LN(BFV, DV, MV) (void)launch_pdl(layernorm_kernel<BFV, DV, MV>, (unsigned)grid, 256u, 0, st, 1, x, in_stride, rows, h, eps, gamma, beta, d, y)
+#define CB_LN_W(BFV, DV) do { if (h <= 512) CB_LN(BFV, DV, 4); else if (h <= 1024) CB_LN(BFV, DV, 8); else CB_LN(BFV, DV, 16); } while (0)
+    if (bf16) { if (d) CB_LN_W(true, true); else CB_LN_W(true, false); }
+    else      { if (d) CB_LN_W(false, true); else CB_LN_W(false, false); }
+#undef CB_LN_W
+#undef CB_LN
 }
 
 void launch_im2col(const float* pixels, int B, int S, int P, int kpad, void* patches16, cudaStream_t st) {
