@@ -66,7 +66,7 @@ EXTENSION_SYMBOLS = [
     "clip_b200_host_malloc", "clip_b200_host_free", "clip_b200_memcpy_h2d", "clip_b200_memcpy_d2h",
     "clip_b200_synchronize", "clip_b200_last_error", "clip_b200_kernel_launches",
     "clip_b200_last_device_ms", "clip_b200_version", "clip_b200_set_micro_batch",
-    "clip_b200_debug_gemm", "clip_b200_get_stream", "clip_b200_kernel_ms",
+    "clip_b200_debug_gemm", "clip_b200_debug_attention", "clip_b200_get_stream", "clip_b200_kernel_ms",
     "clip_b200_debug_repack_roundtrip", "clip_b200_debug_tokenize", "clip_b200_debug_preprocess",
     "clip_b200_mark", "clip_b200_mark_elapsed_ms",
 ]
@@ -166,6 +166,8 @@ class ClipLib:
             L.clip_b200_debug_tokenize.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), ip]
             L.clip_b200_debug_preprocess.restype = C.c_int
             L.clip_b200_debug_preprocess.argtypes = [C.POINTER(C.c_uint8), ip, ip, ip, fp, fp, fp]
+            L.clip_b200_debug_attention.restype = C.c_int
+            L.clip_b200_debug_attention.argtypes = [ip, ip, ip, ip, ip, ip, fp, fp, C.POINTER(C.c_float)]
             L.clip_b200_debug_gemm.restype = C.c_int
             L.clip_b200_debug_gemm.argtypes = [ip, ip, ip, ip, ip, ip, ip, fp, vp, fp, fp, fp, C.POINTER(C.c_float)]
 

@@ -938,6 +938,57 @@ int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int e
 }
 
 
+// TEST HOOK: one attention launch on device 0.  qkv: fp32 host [nseq*T, 3*H*64] (columns Q | K | V, the Q columns already scaled),
+// rounded to the operand type on the way in; out: fp32 host [nseq*T, H*64].  use_legacy=1 runs the mma.sync flash kernel.
+int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int causal, int use_legacy, const float* qkv, float* out, float* ms) {
+    g_err.clear();
+    if (attention_tc_init() != cudaSuccess) { set_err("attention_tc_init failed"); return 1; }
+    if (!use_legacy && !attention_tc_supported(T)) { set_err("T not supported by the tcgen05 attention kernel"); return 2; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, 0);
+    const size_t rows = (size_t)nseq * T, hid = (size_t)H * 64;
+    std::vector<uint16_t> h16(rows * 3 * hid);
+    for (size_t i = 0; i < h16.size(); i++) h16[i] = operand_bf16 ? f32_to_bf16(qkv[i]) : f32_to_f16(qkv[i]);
+    uint16_t *d_qkv = nullptr, *d_out = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = 0;
+    do {
+        cudaError_t e;
+        // pad by one 272-row box: the K/V boxes of the last sequence read (and discard) rows past the end
+        if ((e = cudaMalloc(&d_qkv, (rows + 272) * 3 * hid * 2)) != cudaSuccess || (e = cudaMalloc(&d_out, rows * hid * 2)) != cudaSuccess) { set_err(std::string("cudaMalloc: ") + cudaGetErrorString(e)); rc = 3; break; }
+        cudaMemset(d_qkv, 0, (rows + 272) * 3 * hid * 2);
+        cudaMemset(d_out, 0xff, rows * hid * 2);
+        cudaMemcpy(d_qkv, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice);
+        cudaStreamCreate(&st); cudaEventCreate(&e0); cudaEventCreate(&e1);
+        TmaMap mq, mkv, m16;
+        if (!make_tma_2d_16bit(&mq, d_qkv, rows, 3 * hid, 3 * hid, 128) || !make_tma_2d_16bit(&mkv, d_qkv, rows, 3 * hid, 3 * hid, 256) ||
+            !make_tma_2d_16bit(&m16, d_qkv, rows, 3 * hid, 3 * hid, 16)) { set_err("tensor map failed"); rc = 4; break; }
+        for (int rep = 0; rep < (ms ? 3 : 1); rep++) {
+            cudaEventRecord(e0, st);
+            if (use_legacy) { launch_attention(d_qkv, d_out, nseq, T, H, causal, operand_bf16, 0, st); e = cudaGetLastError(); }
+            else e = launch_attention_tc(&mq, &mkv, &m16, d_out, nseq, T, H, causal, operand_bf16, prop.multiProcessorCount, st);
+            cudaEventRecord(e1, st);
+            if (e != cudaSuccess) break;
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;
+        }
+        if (e != cudaSuccess) { set_err(std::string("attention: ") + cudaGetErrorString(e)); rc = 5; break; }
+        if (ms) cudaEventElapsedTime(ms, e0, e1);
+        std::vector<uint16_t> o16(rows * hid);
+        cudaMemcpy(o16.data(), d_out, o16.size() * 2, cudaMemcpyDeviceToHost);
+        for (size_t i = 0; i < o16.size(); i++) {
+            if (operand_bf16) { uint32_t b = (uint32_t)o16[i] << 16; memcpy(&out[i], &b, 4); }
+            else out[i] = f16_to_f32(o16[i]);
+        }
+    } while (0);
+    cudaFree(d_qkv); cudaFree(d_out);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+
 // ---- CPU-only test hooks (no context / GPU needed) ----------------------------------------------------------
 int clip_b200_debug_repack_roundtrip(int qtype, const void* rows, int N, int K) {
     const size_t raw = (size_t)N * (K / 32) * wpack_ggml_block_bytes(qtype);

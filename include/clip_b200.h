@@ -204,6 +204,12 @@ const char * clip_b200_version(void);
 int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int epi, int use_naive, const float * x,
                          const void * w_rows, const float * bias, const float * resid_in, float * y_out, float * ms);
 
+/* TEST HOOK: one attention launch (clip.cpp:1082-1108 / 1363-1388 semantics: softmax(Q K^T [+ causal mask]) V per head, head_dim 64).
+ * qkv: fp32 host [nseq*T, 3*H*64], columns Q | K | V with the 1/sqrt(64) scale already applied to Q; out: fp32 host [nseq*T, H*64].
+ * use_legacy=1 runs the warp-level mma.sync kernel instead of the tcgen05 one.  ms (optional): device time of the last of 3 launches. */
+int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int causal, int use_legacy, const float * qkv, float * out,
+                              float * ms);
+
 /* CPU-only TEST HOOKS (no context, no GPU): lossless re-tiling check, tokenizer and preprocess without a model context */
 int clip_b200_debug_repack_roundtrip(int qtype, const void * rows, int N, int K);
 int clip_b200_debug_tokenize(const char * gguf_path, const char * text, int32_t * out, int cap);
