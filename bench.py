@@ -307,6 +307,29 @@ def main():
     value = B * world / (ms_step / 1e3)
     e2e = B * world / (ms_e2e / 1e3)
 
+    # ---- N1 leg: raw u8 images in, resize + crop + normalise on the GPU, then the same encode ---------------------
+    e2e_u8 = None
+    if not dist and not args.no_text:
+        SRC = 256
+        rng8 = np.random.default_rng(7)
+        pool = [rng8.integers(0, 256, (SRC, SRC, 3), dtype=np.uint8) for _ in range(16)]
+        items = (bd.clip_image_u8 * B)()
+        for i in range(B):
+            a = pool[i % len(pool)]
+            items[i] = bd.clip_image_u8(SRC, SRC, a.ctypes.data_as(C.POINTER(C.c_uint8)), a.size)
+        batch8 = bd.clip_image_u8_batch(items, B)
+
+        def step_u8():
+            assert L.clip_b200_image_batch_encode_u8(ctx, C.byref(batch8), C.cast(h_out, C.POINTER(C.c_float)), True), lib.last_error()
+
+        step_u8()
+        _, ms_u8 = timed(step_u8, 2)
+        e2e_u8 = {"value": B / (ms_u8 / 1e3), "unit": "img/s", "ms_per_step": ms_u8, "h2d_bytes_per_step": B * SRC * SRC * 3,
+                  "source": "%dx%d u8 RGB per image; resize/crop/normalise on the GPU, bit-identical to clip_image_preprocess; wall clock "
+                            "around clip_b200_image_batch_encode_u8 (includes the host copy into pinned staging)" % (SRC, SRC)}
+        for k in range(4):
+            L.clip_b200_kernel_ms(ctx, k, None)
+
     # ---- secondary line: text-embeddings/sec, 2048 x 77-token sequences per GPU (BASELINE.json configs[3] shape) -------------
     text = None
     if lib.lib.clip_get_text_hparams(ctx).contents.n_layer > 0 and not args.no_text:
@@ -362,7 +385,7 @@ def main():
                          "82-image micro-batch; profiles/r01_gemm_pair_ncu.md) vs %d algorithmic" % ALGO_GEMM_BYTES_PER_LAUNCH,
                          "kernel": "gemm_dq_kernel (all fused-dequant GEMMs of the step)",
                          "flops_per_step": F_GEMM * B, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src},
-            "kernel_time_ms_per_step": kinds, "wall_ms_per_step": ms_wall, "parity": parity, "cpu_baseline": cpu, "text": text,
+            "kernel_time_ms_per_step": kinds, "wall_ms_per_step": ms_wall, "parity": parity, "cpu_baseline": cpu, "text": text, "e2e_u8": e2e_u8,
         }
         print(json.dumps(out), flush=True)
     lib.free(ctx)

@@ -66,7 +66,8 @@ EXTENSION_SYMBOLS = [
     "clip_b200_host_malloc", "clip_b200_host_free", "clip_b200_memcpy_h2d", "clip_b200_memcpy_d2h",
     "clip_b200_synchronize", "clip_b200_last_error", "clip_b200_kernel_launches",
     "clip_b200_last_device_ms", "clip_b200_version", "clip_b200_set_micro_batch",
-    "clip_b200_debug_gemm", "clip_b200_debug_attention", "clip_b200_get_stream", "clip_b200_kernel_ms",
+    "clip_b200_debug_gemm", "clip_b200_debug_attention", "clip_b200_image_batch_encode_u8",
+    "clip_b200_image_batch_preprocess_device", "clip_b200_get_stream", "clip_b200_kernel_ms",
     "clip_b200_debug_repack_roundtrip", "clip_b200_debug_tokenize", "clip_b200_debug_preprocess",
     "clip_b200_mark", "clip_b200_mark_elapsed_ms",
 ]
@@ -166,6 +167,10 @@ class ClipLib:
             L.clip_b200_debug_tokenize.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), ip]
             L.clip_b200_debug_preprocess.restype = C.c_int
             L.clip_b200_debug_preprocess.argtypes = [C.POINTER(C.c_uint8), ip, ip, ip, fp, fp, fp]
+            L.clip_b200_image_batch_encode_u8.restype = C.c_bool
+            L.clip_b200_image_batch_encode_u8.argtypes = [vp, C.POINTER(clip_image_u8_batch), fp, C.c_bool]
+            L.clip_b200_image_batch_preprocess_device.restype = C.c_bool
+            L.clip_b200_image_batch_preprocess_device.argtypes = [vp, C.POINTER(clip_image_u8_batch), C.POINTER(clip_image_f32_batch)]
             L.clip_b200_debug_attention.restype = C.c_int
             L.clip_b200_debug_attention.argtypes = [ip, ip, ip, ip, ip, ip, fp, fp, C.POINTER(C.c_float)]
             L.clip_b200_debug_gemm.restype = C.c_int
@@ -265,6 +270,36 @@ class ClipLib:
         if not self.lib.clip_tokenize(ctx, text.encode(), C.byref(tk)):
             raise RuntimeError("clip_tokenize failed")
         return np.ctypeslib.as_array(tk.data, shape=(tk.size,)).copy()
+
+    def _u8_batch(self, images):
+        """list of [ny, nx, 3] uint8 arrays -> (clip_image_u8_batch, keep-alive objects)"""
+        arrs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        items = (clip_image_u8 * len(arrs))()
+        for i, a in enumerate(arrs):
+            items[i] = clip_image_u8(a.shape[1], a.shape[0], a.ctypes.data_as(C.POINTER(C.c_uint8)), a.size)
+        return clip_image_u8_batch(items, len(arrs)), (arrs, items)
+
+    def image_batch_encode_u8(self, ctx, images, normalize=True) -> np.ndarray:
+        """extension (N1): raw u8 images of any size -> embeddings; resize / crop / normalise run on the GPU"""
+        batch, keep = self._u8_batch(images)
+        d = self.vision_hparams(ctx).projection_dim
+        out = np.empty((len(images), d), np.float32)
+        if not self.lib.clip_b200_image_batch_encode_u8(ctx, C.byref(batch), out.ctypes.data_as(C.POINTER(C.c_float)), normalize):
+            raise RuntimeError("clip_b200_image_batch_encode_u8 failed: " + self.last_error())
+        return out
+
+    def preprocess_device(self, ctx, images) -> np.ndarray:
+        """extension (N1): GPU preprocess alone -> [n, S, S, 3] float32"""
+        batch, keep = self._u8_batch(images)
+        res = (clip_image_f32 * len(images))()
+        outb = clip_image_f32_batch(res, len(images))
+        if not self.lib.clip_b200_image_batch_preprocess_device(ctx, C.byref(batch), C.byref(outb)):
+            raise RuntimeError("clip_b200_image_batch_preprocess_device failed: " + self.last_error())
+        s = res[0].nx
+        out = np.stack([np.ctypeslib.as_array(res[i].data, shape=(s, s, 3)).copy() for i in range(len(images))])
+        for i in range(len(images)):
+            self.lib.clip_image_f32_clean(C.byref(res[i]))
+        return out
 
     def preprocess(self, ctx, img_u8: np.ndarray) -> np.ndarray:
         """img_u8: [ny, nx, 3] uint8 -> [S, S, 3] float32 (clip.cpp:797-927 semantics)."""

@@ -505,6 +505,7 @@ void clip_free(struct clip_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    preprocess_release(c);
     for (void* p : c->allocs) cudaFree(p);
     for (auto& p : c->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -569,6 +570,62 @@ void clip_image_batch_preprocess(const struct clip_ctx* ctx, const int n_threads
     for (int t = 0; t < nt; t++)
         th.emplace_back([=]() { for (size_t i = t; i < n; i += nt) clip_image_preprocess(ctx, &in->data[i], &out->data[i]); });
     for (auto& t : th) t.join();
+}
+
+// ---- N1: preprocess on the device -------------------------------------------------------------------------
+// Shared driver: micro-batches of raw u8 images -> pixel staging buffer (preprocess.cu) -> optional vision forward.
+static bool preprocess_chunks(clip_ctx* c, const clip_image_u8* imgs, size_t n, float* h_pixels_out, float* vec, bool normalize) {
+    Tower& tw = c->vis;
+    if (!ensure_ws(c, tw, tw.micro_batch, tw.T, true)) return false;
+    if (vec && !ensure_out(c, n * tw.proj)) return false;
+    size_t n_chunks, chunk;
+    chunking(n, tw.micro_batch, n_chunks, chunk);
+    const size_t per = (size_t)tw.image_size * tw.image_size * 3;
+    CK(cudaEventRecord(c->ev_t0, c->stream));
+    size_t ci = 0;
+    for (size_t i0 = 0; i0 < n; i0 += chunk, ci++) {
+        const int nb = (int)std::min(chunk, n - i0), b = (int)(ci & 1);
+        if (ci >= 2) CK(cudaEventSynchronize(c->ev_consumed[b]));      // arena b is rewritten on the host below
+        std::string err;
+        if (!preprocess_device(c, imgs + i0, nb, b, tw.ws.pixels[b], c->copy_stream, c->ev_copied[b], c->stream, err)) { set_err(err); return false; }
+        if (h_pixels_out) CK(cudaMemcpyAsync(h_pixels_out + i0 * per, tw.ws.pixels[b], (size_t)nb * per * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (vec && !vision_forward(c, tw.ws.pixels[b], nb, c->d_out + i0 * tw.proj, normalize)) return false;
+        CK(cudaEventRecord(c->ev_consumed[b], c->stream));
+    }
+    CK(cudaEventRecord(c->ev_t1, c->stream));
+    if (vec) CK(cudaMemcpyAsync(vec, c->d_out, n * tw.proj * 4, cudaMemcpyDeviceToHost, c->stream));
+    return sync_and_time(c);
+}
+
+bool clip_b200_image_batch_encode_u8(const struct clip_ctx* cctx, const struct clip_image_u8_batch* imgs, float* vec, const bool normalize) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || !c->has_vision) { set_err("no vision encoder"); return false; }
+    if (!imgs || imgs->size == 0) return true;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    return preprocess_chunks(c, imgs->data, imgs->size, nullptr, vec, normalize);
+}
+
+bool clip_b200_image_batch_preprocess_device(const struct clip_ctx* cctx, const struct clip_image_u8_batch* in, struct clip_image_f32_batch* out) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || !c->has_vision) { set_err("no vision encoder"); return false; }
+    out->size = in->size;
+    const size_t n = in->size;
+    if (n == 0) return true;
+    const int S = c->vhp.image_size;
+    const size_t per = (size_t)3 * S * S;
+    std::vector<float> host(n * per);
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CK(cudaSetDevice(c->device));
+        if (!preprocess_chunks(c, in->data, n, host.data(), nullptr, false)) return false;
+    }
+    for (size_t i = 0; i < n; i++) {        // same ownership convention as clip_image_preprocess: data is new[]-allocated here
+        out->data[i].nx = S; out->data[i].ny = S; out->data[i].size = per;
+        out->data[i].data = new float[per];
+        memcpy(out->data[i].data, host.data() + i * per, per * 4);
+    }
+    return true;
 }
 
 bool clip_b200_image_encode_device(const struct clip_ctx* cctx, const void* d_pixels, size_t n, void* d_vec, bool normalize) {

@@ -215,12 +215,6 @@ std::vector<int32_t> tokenize(const Vocab& v, const char* text) {
 // ascending tap order) so results are bit-identical to the reference (tests/test_host_ops.py).
 // ---------------------------------------------------------------------------------------------------
 namespace {
-struct Taps {
-    int ksize = 0;
-    std::vector<double> k;     // [out][ksize]
-    std::vector<int> lo, cnt;  // first source index, number of taps
-};
-
 inline double keys_cubic(double x) {
     const double a = -0.5;
     if (x < 0.0) x = -x;
@@ -228,42 +222,54 @@ inline double keys_cubic(double x) {
     if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
     return 0.0;
 }
+}  // namespace
 
-Taps make_taps(int in_size, int out_size) {
-    Taps t;
+ResizeTaps resize_taps(int in_size, int out_size, int o0, int n) {
+    ResizeTaps t;
     const float in0 = 0.0f, in1 = (float)in_size;
     double support = 2.0, fs = (double)(in1 - in0) / out_size;
     if (fs < 1.0) fs = 1.0;
     support *= fs;
     t.ksize = (int)ceil(support) * 2 + 1;
-    t.k.assign((size_t)out_size * t.ksize, 0.0);
-    t.lo.resize(out_size);
-    t.cnt.resize(out_size);
+    t.k.assign((size_t)n * t.ksize, 0.0);
+    t.lo.resize(n);
+    t.cnt.resize(n);
     const double ss = 1.0 / fs;
-    for (int o = 0; o < out_size; o++) {
+    for (int i = 0; i < n; i++) {
+        const int o = o0 + i;
         const double center = in0 + (o + 0.5) * (in1 - in0) / out_size;
         int lo = (int)(center - support + 0.5);
         if (lo < 0) lo = 0;
         int hi = (int)(center + support + 0.5);
         if (hi > in_size) hi = in_size;
         const int cnt = hi - lo;
-        double* k = &t.k[(size_t)o * t.ksize];
+        double* k = &t.k[(size_t)i * t.ksize];
         double ww = 0.0;
         for (int x = 0; x < cnt; x++) { const double w = keys_cubic((x + lo - center + 0.5) * ss); k[x] = w; ww += w; }
         if (ww != 0.0) for (int x = 0; x < cnt; x++) k[x] /= ww;
-        t.lo[o] = lo;
-        t.cnt[o] = cnt;
+        t.lo[i] = lo;
+        t.cnt[i] = cnt;
     }
     return t;
 }
+
+bool preprocess_geometry(int nx, int ny, int S, int* nx3, int* ny3) {
+    if (nx <= 0 || ny <= 0 || S <= 0) return false;
+    const float scale = std::min((float)nx, (float)ny) / (float)S;
+    *nx3 = (int)(nx / scale + 0.5f);
+    *ny3 = (int)(ny / scale + 0.5f);
+    return *nx3 >= S && *ny3 >= S;
+}
+
+namespace {
+typedef ResizeTaps Taps;
+inline Taps make_taps(int in_size, int out_size) { return resize_taps(in_size, out_size, 0, out_size); }
 inline float clamp255(double v) { return std::min(std::max((float)v, 0.0f), 255.0f); }
 }  // namespace
 
 bool preprocess_image(const uint8_t* src, int nx, int ny, int S, const float mean[3], const float stdv[3], float* dst) {
-    if (!src || nx <= 0 || ny <= 0 || S <= 0) return false;
-    const float scale = std::min((float)nx, (float)ny) / (float)S;
-    const int nx3 = (int)(nx / scale + 0.5f), ny3 = (int)(ny / scale + 0.5f);
-    if (nx3 < S || ny3 < S) return false;
+    int nx3 = 0, ny3 = 0;
+    if (!src || !preprocess_geometry(nx, ny, S, &nx3, &ny3)) return false;
     const Taps th = make_taps(nx, nx3), tv = make_taps(ny, ny3);
     std::vector<float> tmp((size_t)3 * nx3 * ny), res((size_t)3 * nx3 * ny3);
     for (int y = 0; y < ny; y++)

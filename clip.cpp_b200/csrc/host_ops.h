@@ -24,6 +24,17 @@ struct Vocab {
 // clip_tokenize (clip.cpp:598-679): regex word split, whole-word "</w>" lookup, greedy longest match, SOT/EOT
 std::vector<int32_t> tokenize(const Vocab& v, const char* text);
 
+// resize geometry and bicubic taps of clip_image_preprocess (clip.cpp:743-794, 797-853), shared with the device-side preprocess
+// (preprocess.cu): taps for the output positions [o0, o0 + n) of one axis, k[i * ksize + t] in double exactly as the reference
+// normalises them; lo[i] = first source index, cnt[i] = number of taps.
+struct ResizeTaps {
+    int ksize = 0;
+    std::vector<double> k;
+    std::vector<int> lo, cnt;
+};
+ResizeTaps resize_taps(int in_size, int out_size, int o0, int n);
+bool preprocess_geometry(int nx, int ny, int S, int* nx3, int* ny3);   // false when the resized image would be smaller than S
+
 // clip_image_preprocess (clip.cpp:797-927)
 bool preprocess_image(const uint8_t* src, int nx, int ny, int out_size, const float mean[3], const float stdv[3], float* dst);
 

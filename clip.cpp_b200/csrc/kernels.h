@@ -49,6 +49,16 @@ void launch_gather_rows(const float* src, float* dst, int rows, int h, int strid
 void launch_logits(const float* img, const float* txt, float* logits, int n_img, int n_txt, int d, cudaStream_t st);
 void launch_softmax_plain(float* logits, int rows, int cols, cudaStream_t st);
 
+}  // namespace cb
+struct clip_ctx;
+struct clip_image_u8;
+#include <string>
+namespace cb {
+// N1 device-side preprocess (preprocess.cu): raw u8 images -> [nb, S, S, 3] fp32 crops, bit-identical to host_ops.cpp: preprocess_image
+bool preprocess_device(clip_ctx* c, const clip_image_u8* imgs, int nb, int buf, float* d_pixels, cudaStream_t copy_st, cudaEvent_t copied,
+                       cudaStream_t st, std::string& err);
+void preprocess_release(clip_ctx* c);
+
 // DEBUG ONLY (tests / CLIP_B200_DEBUG_NAIVE=1): scalar GEMM straight from ggml-format rows on the device.
 void launch_naive_gemm(const void* x16, int x_bf16, const void* w_ggml, int qtype, const float* bias, void* out, int M, int N,
                        int K, int ldo, int epi, int out_bf16, int scale_cols, float scale, cudaStream_t st);

@@ -69,6 +69,14 @@ struct Tower {
 
 struct ProfEvent { int kind; cudaEvent_t e0, e1; };
 
+struct PreArena {                // staging of the device-side preprocess (preprocess.cu), one per pixel staging buffer
+    uint8_t* h = nullptr;        // pinned: descriptors, tap tables, raw u8 pixels of one micro-batch
+    uint8_t* d = nullptr;        // device copy of the blob
+    size_t cap = 0, last_bytes = 0;
+    float* d_tmp = nullptr;      // horizontally resized rows
+    size_t tmp_cap = 0;          // in floats
+};
+
 }  // namespace cb
 
 struct clip_ctx {
@@ -90,5 +98,6 @@ struct clip_ctx {
     float last_ms = 0.f;
     std::vector<cb::ProfEvent> prof;
     std::vector<cudaEvent_t> ev_pool;
+    cb::PreArena pre[2];
     std::mutex mu;
 };

@@ -204,6 +204,15 @@ const char * clip_b200_version(void);
 int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int epi, int use_naive, const float * x,
                          const void * w_rows, const float * bias, const float * resid_in, float * y_out, float * ms);
 
+/* N1 -- clip_image_batch_preprocess (clip.h:98, clip.cpp:963-1008) on the device, fused with the encode:
+ * raw u8 RGB images of any size are uploaded (3 B/pixel), resized (PIL-style antialiased bicubic, a = -0.5), centre-cropped and
+ * normalised on the GPU -- bit-identical to clip_image_preprocess -- and encoded like clip_image_batch_encode (clip.h:104). */
+bool clip_b200_image_batch_encode_u8(const struct clip_ctx * ctx, const struct clip_image_u8_batch * imgs, float * vec, const bool normalize);
+/* the device preprocess alone, results copied back into new[]-allocated clip_image_f32 buffers exactly like
+ * clip_image_batch_preprocess fills them (clip.cpp:985-1007) */
+bool clip_b200_image_batch_preprocess_device(const struct clip_ctx * ctx, const struct clip_image_u8_batch * in,
+                                             struct clip_image_f32_batch * out);
+
 /* TEST HOOK: one attention launch (clip.cpp:1082-1108 / 1363-1388 semantics: softmax(Q K^T [+ causal mask]) V per head, head_dim 64).
  * qkv: fp32 host [nseq*T, 3*H*64], columns Q | K | V with the 1/sqrt(64) scale already applied to Q; out: fp32 host [nseq*T, H*64].
  * use_legacy=1 runs the warp-level mma.sync kernel instead of the tcgen05 one.  ms (optional): device time of the last of 3 launches. */
