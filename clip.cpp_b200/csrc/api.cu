@@ -334,7 +334,10 @@ bool ensure_out(clip_ctx* c, size_t floats) {
 }
 
 int default_micro_batch(int T) {   // 37 token tiles = 148/4: every N/128 that is a multiple of 4 fills whole waves
-    int waves = 3;   // measured on B200 (ViT-L/14 q4_0, b=512): 1 -> 3794, 2 -> 4188, 3 -> 4270 img/s
+    // measured on B200 (ViT-L/14 q4_0, b=512, final kernels): 3 -> 4914, 4 -> 5062, 8 -> 5219, 12 -> 5316 img/s, one chunk of 512 -> 5394
+    // device-resident but 5298 end to end (the H2D copy of a single chunk cannot hide under compute).  Fewer, longer launches: the
+    // ~3 us drain/fill gap per launch is paid 1200 times per 512 images at 3 waves.  12 waves = 331 ViT-L/14 images = 1.9 GB of workspace.
+    int waves = 12;
     if (const char* e = getenv("CLIP_B200_TOKEN_TILES_X37")) waves = std::max(1, atoi(e));
     const int mb = 37 * waves * GEMM_BN / T;
     return mb < 1 ? 1 : mb;
