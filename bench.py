@@ -178,11 +178,12 @@ def run_reference_arm(args, rank, world):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_dq_kernel, from the committed `ncu --set full` capture of the four
-# layer GEMM shapes (QKV, out-proj, FC1, FC2) at the 82-image micro-batch: (206.1 + 125.7 + 51.3 + 164.4) MB / 4.  It is BELOW the
-# algorithmic bytes (X once + packed W once + Y once = 174 MB mean) because part of each output is still in the 126 MB L2 when the
-# kernel ends and the activations written by the previous kernel are read from L2.
-NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 136_900_000
-ALGO_GEMM_BYTES_PER_LAUNCH = 174_300_000
+# layer GEMM shapes (FC2, QKV, out-proj, FC1) at the 256-image micro-batch this workload runs with (65792 token rows):
+# (664.1 + 488.2 + 233.7 + 622.8) MB / 4.  It is BELOW the algorithmic bytes (X once + packed W once + Y once = 540.8 MB mean):
+# activations written by the previous kernel are partly read from the 126 MB L2 and part of each output is still in L2 when
+# the kernel retires.  profiles/r01_gemm_pair_ncu.md has the per-launch table.
+NCU_GEMM_DRAM_BYTES_PER_LAUNCH = 502_200_000
+ALGO_GEMM_BYTES_PER_LAUNCH = 540_800_000
 
 
 def main():
@@ -382,7 +383,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": NCU_GEMM_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes/launch (dram read+write, mean of the 4 layer GEMM shapes, "
-                         "82-image micro-batch; profiles/r01_gemm_pair_ncu.md) vs %d algorithmic" % ALGO_GEMM_BYTES_PER_LAUNCH,
+                         "256-image micro-batch; profiles/r01_gemm_pair_ncu.md) vs %d algorithmic" % ALGO_GEMM_BYTES_PER_LAUNCH,
                          "kernel": "gemm_dq_kernel (all fused-dequant GEMMs of the step)",
                          "flops_per_step": F_GEMM * B, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src},
             "kernel_time_ms_per_step": kinds, "wall_ms_per_step": ms_wall, "parity": parity, "cpu_baseline": cpu, "text": text, "e2e_u8": e2e_u8,
