@@ -96,3 +96,16 @@ def test_many_items_per_cta(prod, T, causal, nseq, H):
     qkv = rng.standard_normal((nseq * T, 3 * H * 64)).astype(np.float32)
     qkv[:, : H * 64] *= 0.3
     check(prod, qkv, nseq, T, H, causal, 1)
+
+
+@pytest.mark.parametrize("T,causal", [(300, 0), (577, 0), (100, 1)])
+def test_legacy_kernel_long_sequences(prod, T, causal):
+    """T > 257 (e.g. ViT-L/14@336: 577 tokens) is served by the warp-level mma.sync flash kernel."""
+    rng = np.random.default_rng(T)
+    nseq, H = 2, 3
+    qkv = rng.standard_normal((nseq * T, 3 * H * 64)).astype(np.float32)
+    qkv[:, : H * 64] *= 0.3
+    got = run(prod, qkv, nseq, T, H, causal, 1, legacy=1)
+    want = ref_attention(qkv, nseq, T, H, causal, 1)
+    assert np.abs(got - want).max() / (np.abs(want).max() + 1e-6) < 2e-2
+    assert one_minus_cos(got.ravel(), want.ravel()) < 1e-4
