@@ -27,6 +27,7 @@ def _images(sizes, seed):
 @pytest.fixture(scope="module")
 def ctx(prod):
     c = prod.load(model_file("tiny", "f16", prod), 0)
+    prod.lib.clip_b200_set_micro_batch(c, 64, 0)        # 700 images below = 11 micro-batches through both staging arenas
     yield c
     prod.free(c)
 
