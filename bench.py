@@ -58,7 +58,7 @@ def ensure_model(lib, rank):
         os.replace(f16 + ".tmp", f16)
         log("bench: wrote %s in %.1fs" % (f16, time.time() - t0))
     t0 = time.time()
-    # clip_model_quantize of the product library (byte-identical to the reference's: tests/test_quantize.py)
+    # clip_model_quantize of the product library (byte-identical to the reference's: tests/test_host_side.py)
     assert lib.quantize(f16, path + ".tmp", 2), "quantize failed"
     os.replace(path + ".tmp", path)
     log("bench: quantized to %s in %.1fs" % (path, time.time() - t0))

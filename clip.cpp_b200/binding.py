@@ -4,7 +4,7 @@ The same `ClipLib` class drives either shared library, because the product keeps
 22 exported symbols and struct layouts byte for byte:
 
   * `libclip_b200.so`        -- the B200-native product (this repository)
-  * `oracle/_ref/libclip_ref.so` -- the unmodified reference, used by tests/bench as the checker
+  * the unmodified reference built under oracle/ (path: oracle/ref_run.py REF_LIB) -- tests / bench use it as the checker
 
 It mirrors the shape of the reference's own Python binding
 (/root/reference/examples/python_bindings/clip_cpp/clip.py:36-208) but carries the `size` members of
@@ -70,11 +70,15 @@ EXTENSION_SYMBOLS = [
     "clip_b200_image_batch_preprocess_device", "clip_b200_get_stream", "clip_b200_kernel_ms",
     "clip_b200_debug_repack_roundtrip", "clip_b200_debug_tokenize", "clip_b200_debug_preprocess",
     "clip_b200_mark", "clip_b200_mark_elapsed_ms",
+    # scoring + multi-GPU (round 2)
+    "clip_b200_topk_search", "clip_b200_zero_shot_images", "clip_b200_dist_unique_id", "clip_b200_dist_init_with_id",
+    "clip_b200_dist_init", "clip_b200_dist_rank", "clip_b200_dist_world", "clip_b200_device_count", "clip_b200_nccl_version", "clip_b200_cuda_device_count",
+    "clip_b200_dist_barrier", "clip_b200_dist_max_f64", "clip_b200_dist_all_gather", "clip_b200_image_encode_device_all",
+    "clip_b200_text_encode_device_all", "clip_b200_image_batch_encode_all", "clip_b200_text_batch_encode_all",
 ]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PRODUCT_LIB = os.path.join(HERE, "libclip_b200.so")
-REF_LIB = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libclip_ref.so")
 
 
 class ClipLib:
@@ -175,6 +179,39 @@ class ClipLib:
             L.clip_b200_debug_attention.argtypes = [ip, ip, ip, ip, ip, ip, fp, fp, C.POINTER(C.c_float)]
             L.clip_b200_debug_gemm.restype = C.c_int
             L.clip_b200_debug_gemm.argtypes = [ip, ip, ip, ip, ip, ip, ip, fp, vp, fp, fp, fp, C.POINTER(C.c_float)]
+            ipp = C.POINTER(C.c_int)
+            L.clip_b200_topk_search.restype = C.c_bool
+            L.clip_b200_topk_search.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, ip, fp, ipp]
+            L.clip_b200_zero_shot_images.restype = C.c_bool
+            L.clip_b200_zero_shot_images.argtypes = [vp, ip, C.POINTER(clip_image_f32_batch), C.POINTER(clip_tokens), C.c_size_t,
+                                                     C.c_bool, ip, fp, ipp]
+            L.clip_b200_dist_unique_id.restype = C.c_bool
+            L.clip_b200_dist_unique_id.argtypes = [vp]
+            L.clip_b200_dist_init_with_id.restype = C.c_bool
+            L.clip_b200_dist_init_with_id.argtypes = [vp, ip, ip, vp]
+            L.clip_b200_dist_init.restype = C.c_bool
+            L.clip_b200_dist_init.argtypes = [vp, ip, ip, C.c_char_p]
+            for f in ("clip_b200_dist_rank", "clip_b200_dist_world", "clip_b200_device_count"):
+                getattr(L, f).restype = C.c_int
+                getattr(L, f).argtypes = [vp]
+            L.clip_b200_nccl_version.restype = C.c_int
+            L.clip_b200_nccl_version.argtypes = []
+            L.clip_b200_cuda_device_count.restype = C.c_int
+            L.clip_b200_cuda_device_count.argtypes = []
+            L.clip_b200_dist_barrier.restype = C.c_bool
+            L.clip_b200_dist_barrier.argtypes = [vp]
+            L.clip_b200_dist_max_f64.restype = C.c_bool
+            L.clip_b200_dist_max_f64.argtypes = [vp, C.POINTER(C.c_double), ip]
+            L.clip_b200_dist_all_gather.restype = C.c_bool
+            L.clip_b200_dist_all_gather.argtypes = [vp, vp, vp, C.c_size_t]
+            L.clip_b200_image_encode_device_all.restype = C.c_bool
+            L.clip_b200_image_encode_device_all.argtypes = [vp, vp, C.c_size_t, vp, C.c_bool]
+            L.clip_b200_text_encode_device_all.restype = C.c_bool
+            L.clip_b200_text_encode_device_all.argtypes = [vp, vp, vp, C.c_size_t, ip, vp, C.c_bool]
+            L.clip_b200_image_batch_encode_all.restype = C.c_bool
+            L.clip_b200_image_batch_encode_all.argtypes = [vp, ip, C.POINTER(clip_image_f32_batch), fp, C.c_bool]
+            L.clip_b200_text_batch_encode_all.restype = C.c_bool
+            L.clip_b200_text_batch_encode_all.argtypes = [vp, ip, C.POINTER(clip_tokens), C.c_size_t, fp, C.c_bool]
 
     # ---- model -----------------------------------------------------------------------------------
     def load(self, path: str, verbosity: int = 0):
@@ -264,6 +301,49 @@ class ClipLib:
         if not ok:
             raise RuntimeError("clip_text_batch_encode failed: " + self.last_error())
         return out
+
+    @staticmethod
+    def make_token_array(seqs):
+        seqs = [np.ascontiguousarray(s, np.int32) for s in seqs]
+        arr = (clip_tokens * max(len(seqs), 1))()
+        for i, s in enumerate(seqs):
+            arr[i].data = s.ctypes.data_as(C.POINTER(C.c_int32))
+            arr[i].size = s.size
+        return arr, seqs
+
+    def zero_shot_images(self, ctx, images: np.ndarray, label_seqs, top_k: int, normalize=False, n_threads=4):
+        """extension: batch form of clip_zero_shot_label_image -> (scores [n, k], indices [n, k]); labels are token arrays.
+        In ranks mode `label_seqs` is this rank's shard and the result ranks ALL ranks' labels (index = rank * len + j)."""
+        batch, keep = self.make_image_batch(images)
+        arr, keep2 = self.make_token_array(label_seqs)
+        n_all = len(label_seqs) * max(1, self.lib.clip_b200_dist_world(ctx))
+        k = n_all if top_k <= 0 or top_k > n_all else top_k
+        scores = np.empty((images.shape[0], k), np.float32)
+        idx = np.empty((images.shape[0], k), np.int32)
+        ok = self.lib.clip_b200_zero_shot_images(ctx, n_threads, C.byref(batch), arr, len(label_seqs), normalize, k,
+                                                 scores.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int)))
+        if not ok:
+            raise RuntimeError("clip_b200_zero_shot_images failed: " + self.last_error())
+        return scores, idx
+
+    def compare_text_and_image(self, ctx, text: str, img_u8: np.ndarray, n_threads=4) -> float:
+        img_u8 = np.ascontiguousarray(img_u8, np.uint8)
+        src = clip_image_u8(img_u8.shape[1], img_u8.shape[0], img_u8.ctypes.data_as(C.POINTER(C.c_uint8)), img_u8.size)
+        score = C.c_float(0)
+        if not self.lib.clip_compare_text_and_image(ctx, n_threads, text.encode(), C.byref(src), C.byref(score)):
+            raise RuntimeError("clip_compare_text_and_image failed: " + self.last_error())
+        return float(score.value)
+
+    def zero_shot_label_image(self, ctx, img_u8: np.ndarray, labels, n_threads=4):
+        img_u8 = np.ascontiguousarray(img_u8, np.uint8)
+        src = clip_image_u8(img_u8.shape[1], img_u8.shape[0], img_u8.ctypes.data_as(C.POINTER(C.c_uint8)), img_u8.size)
+        arr = (C.c_char_p * len(labels))(*[l.encode() for l in labels])
+        scores = np.empty(len(labels), np.float32)
+        idx = np.empty(len(labels), np.int32)
+        if not self.lib.clip_zero_shot_label_image(ctx, n_threads, C.byref(src), arr, len(labels),
+                                                   scores.ctypes.data_as(C.POINTER(C.c_float)), idx.ctypes.data_as(C.POINTER(C.c_int))):
+            raise RuntimeError("clip_zero_shot_label_image failed: " + self.last_error())
+        return scores, idx
 
     def tokenize(self, ctx, text: str) -> np.ndarray:
         tk = clip_tokens()

@@ -75,7 +75,14 @@ struct Scope {
         if (c->profile) { e0 = get_event(c); cudaEventRecord(e0, c->stream); }
     }
     ~Scope() {
-        if (c->profile) { cudaEvent_t e1 = get_event(c); cudaEventRecord(e1, c->stream); c->prof.push_back({kind, e0, e1}); }
+        if (!c->profile) return;
+        cudaEvent_t e1 = get_event(c);
+        cudaEventRecord(e1, c->stream);
+        c->prof.push_back({kind, e0, e1});
+        if (c->prof.size() > 65536) {        // nobody drains the records: recycle the older half instead of growing without bound
+            for (size_t i = 0; i < 32768; i++) { c->ev_pool.push_back(c->prof[i].e0); c->ev_pool.push_back(c->prof[i].e1); }
+            c->prof.erase(c->prof.begin(), c->prof.begin() + 32768);
+        }
     }
 };
 enum { K_GEMM = 0, K_ATTN = 1, K_LN = 2, K_OTHER = 3 };
@@ -205,6 +212,7 @@ bool load_blocks(clip_ctx* c, const GgufFile& g, const char* p, Tower& tw) {
 }
 
 bool check_geometry(const char* what, const Tower& t) {
+    if (t.hidden <= 0 || t.ff <= 0 || t.heads <= 0 || t.layers < 0 || t.layers > 1024 || t.proj <= 0 || !(t.eps >= 0.f)) { set_err(std::string(what) + ": non-positive hyper-parameter in the file"); return false; }
     if (t.heads <= 0 || t.hidden % t.heads || t.hidden / t.heads != 64) { set_err(std::string(what) + ": head_dim must be 64 (hidden " + std::to_string(t.hidden) + ", heads " + std::to_string(t.heads) + ")"); return false; }
     if (t.hidden > 2048) { set_err(std::string(what) + ": hidden size > 2048 is not supported by the register-resident LayerNorm"); return false; }
     if (t.hidden % 128 || t.ff % 128 || t.proj % 128) { set_err(std::string(what) + ": hidden/ff/projection sizes must be multiples of 128"); return false; }
@@ -325,13 +333,24 @@ bool text_forward(clip_ctx* c, int nb, int T, float* d_out, bool normalize) {
     return true;
 }
 
-bool ensure_out(clip_ctx* c, size_t floats) {
-    if (c->d_out_cap >= floats) return true;
-    float* p = nullptr;
-    if (!dev_alloc(c, &p, floats)) return false;   // old buffer stays in allocs until clip_free (grow-only, rare)
-    c->d_out = p; c->d_out_cap = floats;
+void dev_free(clip_ctx* c, void* p) {
+    if (!p) return;
+    auto it = std::find(c->allocs.begin(), c->allocs.end(), p);
+    if (it != c->allocs.end()) c->allocs.erase(it);
+    cudaFree(p);
+}
+// grow-only device buffer; the outgrown one is released once the stream has drained (nothing may still read it)
+template <class T>
+bool ensure_buf(clip_ctx* c, T** buf, size_t* cap, size_t count) {
+    if (*cap >= count) return true;
+    const size_t want = std::max(count, *cap + *cap / 2);
+    T* p = nullptr;
+    if (!dev_alloc(c, &p, want)) return false;
+    if (*buf) { cudaStreamSynchronize(c->stream); dev_free(c, *buf); }
+    *buf = p; *cap = want;
     return true;
 }
+bool ensure_out(clip_ctx* c, size_t floats) { return ensure_buf(c, &c->d_out, &c->d_out_cap, floats); }
 
 int default_micro_batch(int T) {   // 37 token tiles = 148/4: every N/128 that is a multiple of 4 fills whole waves
     // measured on B200 (ViT-L/14 q4_0, b=512, final kernels): 3 -> 4914, 4 -> 5062, 8 -> 5219, 12 -> 5316 img/s, one chunk of 512 -> 5394
@@ -370,6 +389,35 @@ bool image_encode_device_locked(clip_ctx* c, const float* d_pixels, size_t n, fl
     return true;
 }
 
+// ---- devices mode helper: f(replica, r, lo, hi) on one host thread per GPU, contiguous balanced shards of n items --------------
+template <class F>
+bool for_each_replica(clip_ctx* c, size_t n, F f) {
+    const int w = (int)c->replicas.size();
+    std::vector<std::string> errs((size_t)w);
+    std::vector<char> ok((size_t)w, 1);
+    std::vector<std::thread> th;
+    for (int r = 0; r < w; r++) {
+        size_t lo, hi;
+        shard_bounds(n, r, w, lo, hi);
+        th.emplace_back([&, r, lo, hi]() {
+            g_err.clear();
+            ok[r] = f(c->replicas[r], r, lo, hi) ? 1 : 0;
+            if (!ok[r]) errs[r] = g_err;
+        });
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(c->device);
+    for (int r = 0; r < w; r++)
+        if (!ok[r]) { set_err("device " + std::to_string(c->replicas[r]->device) + ": " + errs[r]); return false; }
+    return true;
+}
+
+bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 }  // namespace
 
 // =====================================================================================================================
@@ -380,19 +428,12 @@ extern "C" {
 const char* clip_b200_last_error(void) { return g_err.c_str(); }
 const char* clip_b200_version(void) { return "clip_b200 0.1 (sm_100a; tcgen05 fused-dequant GEMM)"; }
 
-struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
-    try {
-        g_err.clear();
-        int ndev = 0;
-        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device: libclip_b200 has no CPU path"); return nullptr; }
-        GgufFile g;
-        std::string err;
-        if (!g.parse(fname, err)) { set_err(err); return nullptr; }
+// one replica of the model on `device` (weights are <= 0.33 GB: replicated, never sharded -- SURVEY.md section 8e)
+static clip_ctx* load_on_device(const GgufFile& g, int device, const int verbosity) {
+    {
         std::unique_ptr<clip_ctx, void (*)(clip_ctx*)> guard(new clip_ctx, [](clip_ctx* p) { clip_free(p); });
         clip_ctx* c = guard.get();
-        const char* dv = getenv("CLIP_B200_DEVICE");
-        c->device = dv ? atoi(dv) : 0;
-        if (c->device < 0 || c->device >= ndev) { set_err("CLIP_B200_DEVICE out of range"); return nullptr; }
+        c->device = device;
         if (cudaSetDevice(c->device) != cudaSuccess) { set_err("cudaSetDevice failed"); return nullptr; }
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, c->device) != cudaSuccess) { set_err("cudaGetDeviceProperties failed"); return nullptr; }
@@ -417,15 +458,15 @@ struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
             const GgufKV* nm = g.find("general.name");
             const GgufKV* ds = g.find("general.description");
             const GgufKV* ft = g.find("general.file_type");
-            if (nm) printf("%s: model name:   %s\n", __func__, nm->s.c_str());
-            if (ds) printf("%s: description:  %s\n", __func__, ds->s.c_str());
-            printf("%s: GGUF version: %u\n", __func__, g.version);
-            printf("%s: alignment:    %zu\n", __func__, g.alignment);
-            printf("%s: n_tensors:    %zu\n", __func__, g.tensors.size());
-            printf("%s: n_kv:         %zu\n", __func__, g.kvs.size());
-            if (ft) printf("%s: ftype:        %d\n", __func__, (int)ft->u);
-            printf("%s: text_encoder:   %d\n%s: vision_encoder: %d\n", __func__, c->has_text, __func__, c->has_vision);
-            printf("%s: device:       %d (%s, %d SMs)\n", __func__, c->device, prop.name, c->num_sms);
+            if (nm) printf("%s: model name:   %s\n", "clip_model_load", nm->s.c_str());
+            if (ds) printf("%s: description:  %s\n", "clip_model_load", ds->s.c_str());
+            printf("%s: GGUF version: %u\n", "clip_model_load", g.version);
+            printf("%s: alignment:    %zu\n", "clip_model_load", g.alignment);
+            printf("%s: n_tensors:    %zu\n", "clip_model_load", g.tensors.size());
+            printf("%s: n_kv:         %zu\n", "clip_model_load", g.kvs.size());
+            if (ft) printf("%s: ftype:        %d\n", "clip_model_load", (int)ft->u);
+            printf("%s: text_encoder:   %d\n%s: vision_encoder: %d\n", "clip_model_load", c->has_text, "clip_model_load", c->has_vision);
+            printf("%s: device:       %d (%s, %d SMs)\n", "clip_model_load", c->device, prop.name, c->num_sms);
         }
 
         if (c->has_text) {
@@ -442,6 +483,7 @@ struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
             c->vocab.n = hp.n_vocab;
             t.present = true; t.hidden = hp.hidden_size; t.ff = hp.n_intermediate; t.heads = hp.n_head; t.layers = hp.n_layer;
             t.proj = hp.projection_dim; t.eps = hp.eps; t.n_vocab = hp.n_vocab; t.n_ctx = hp.num_positions;
+            if (t.n_ctx <= 0 || t.n_ctx > 4096 || t.n_vocab <= 0) { set_err("text tower: bad context_length / vocabulary size"); return nullptr; }
             if (!check_geometry("text tower", t)) return nullptr;
             if (!upload_f32(c, g, "t.token_embd.weight", &t.tok, (int64_t)t.n_vocab * t.hidden) ||
                 !upload_f32(c, g, "t.position_embd.weight", &t.pos, (int64_t)t.n_ctx * t.hidden) ||
@@ -451,7 +493,7 @@ struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
             t.micro_batch = default_micro_batch(t.n_ctx);
             if (verbosity >= 2)
                 printf("\n%s: text model hparams\nn_vocab            %d\nnum_positions      %d\nt_hidden_size      %d\nt_n_intermediate   %d\nt_projection_dim   %d\nt_n_head           %d\nt_n_layer          %d\n",
-                       __func__, hp.n_vocab, hp.num_positions, hp.hidden_size, hp.n_intermediate, hp.projection_dim, hp.n_head, hp.n_layer);
+                       "clip_model_load", hp.n_vocab, hp.num_positions, hp.hidden_size, hp.n_intermediate, hp.projection_dim, hp.n_head, hp.n_layer);
         }
         if (c->has_vision) {
             Tower& t = c->vis;
@@ -469,7 +511,7 @@ struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
             memcpy(c->image_std, ks->raw + 12, 12);
             t.present = true; t.hidden = hp.hidden_size; t.ff = hp.n_intermediate; t.heads = hp.n_head; t.layers = hp.n_layer;
             t.proj = hp.projection_dim; t.eps = hp.eps; t.image_size = hp.image_size; t.patch = hp.patch_size;
-            if (t.patch <= 0 || t.image_size % t.patch) { set_err("image_size must be a multiple of patch_size"); return nullptr; }
+            if (t.patch <= 0 || t.image_size <= 0 || t.image_size > 4096 || t.image_size % t.patch) { set_err("image_size must be a positive multiple of patch_size"); return nullptr; }
             t.n_patches = (t.image_size / t.patch) * (t.image_size / t.patch);
             t.T = t.n_patches + 1;
             t.kpad = (3 * t.patch * t.patch + GEMM_BK - 1) / GEMM_BK * GEMM_BK;
@@ -485,7 +527,7 @@ struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
             t.micro_batch = default_micro_batch(t.T);
             if (verbosity >= 2)
                 printf("\n%s: vision model hparams\nimage_size         %d\npatch_size         %d\nv_hidden_size      %d\nv_n_intermediate   %d\nv_projection_dim   %d\nv_n_head           %d\nv_n_layer          %d\n",
-                       __func__, hp.image_size, hp.patch_size, hp.hidden_size, hp.n_intermediate, hp.projection_dim, hp.n_head, hp.n_layer);
+                       "clip_model_load", hp.image_size, hp.patch_size, hp.hidden_size, hp.n_intermediate, hp.projection_dim, hp.n_head, hp.n_layer);
         }
         // 16-bit operand type of the towers: fp16 when any tower GEMM weight is stored unquantized (the reference rounds
         // those activations to fp16 too, ggml.c:11333-11349); bf16 for fully quantized towers unless overridden.
@@ -495,9 +537,74 @@ struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
             if (!strcmp(op, "f16")) c->operand_bf16 = false;
             else if (!strcmp(op, "bf16") && !f16w) c->operand_bf16 = true;
         }
-        if (verbosity >= 1) printf("%s: operand type: %s%s\n", __func__, c->operand_bf16 ? "bf16" : "fp16", c->debug_naive ? "  [DEBUG naive GEMM]" : "");
+        if (verbosity >= 1) printf("%s: operand type: %s%s\n", "clip_model_load", c->operand_bf16 ? "bf16" : "fp16", c->debug_naive ? "  [DEBUG naive GEMM]" : "");
         if (cudaDeviceSynchronize() != cudaSuccess) { set_err("upload failed"); return nullptr; }
         return guard.release();
+    }
+}
+
+// CLIP_B200_DEVICES = "all" | "0,1,2,..." -> devices mode (several GPUs behind ONE context); otherwise CLIP_B200_DEVICE (default 0),
+// or LOCAL_RANK when CLIP_B200_DIST=env asks the context to join the launcher's ranks (torchrun / mpirun style environment).
+static bool parse_devices(int ndev, std::vector<int>& out) {
+    out.clear();
+    const char* dl = getenv("CLIP_B200_DEVICES");
+    if (dl && *dl) {
+        if (!strcmp(dl, "all")) { for (int i = 0; i < ndev; i++) out.push_back(i); return true; }
+        const char* p = dl;
+        while (*p) {
+            char* e = nullptr;
+            const long v = strtol(p, &e, 10);
+            if (e == p || v < 0 || v >= ndev) { set_err(std::string("CLIP_B200_DEVICES: bad device list '") + dl + "'"); return false; }
+            if (std::find(out.begin(), out.end(), (int)v) != out.end()) { set_err("CLIP_B200_DEVICES: duplicate device"); return false; }
+            out.push_back((int)v);
+            p = (*e == ',') ? e + 1 : e;
+            if (*e && *e != ',') { set_err(std::string("CLIP_B200_DEVICES: bad device list '") + dl + "'"); return false; }
+        }
+        if (out.empty()) { set_err("CLIP_B200_DEVICES: empty device list"); return false; }
+        return true;
+    }
+    const char* dist_env = getenv("CLIP_B200_DIST");
+    const char* dv = getenv("CLIP_B200_DEVICE");
+    int d = dv ? atoi(dv) : 0;
+    if (!dv && dist_env && !strcmp(dist_env, "env") && getenv("LOCAL_RANK")) d = atoi(getenv("LOCAL_RANK"));
+    if (d < 0 || d >= ndev) { set_err("CLIP_B200_DEVICE out of range"); return false; }
+    out.push_back(d);
+    return true;
+}
+
+struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
+    try {
+        g_err.clear();
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { set_err("no CUDA device: libclip_b200 has no CPU path"); return nullptr; }
+        GgufFile g;
+        std::string err;
+        if (!g.parse(fname, err)) { set_err(err); return nullptr; }
+        std::vector<int> devs;
+        if (!parse_devices(ndev, devs)) return nullptr;
+        std::unique_ptr<clip_ctx, void (*)(clip_ctx*)> leader(load_on_device(g, devs[0], verbosity), [](clip_ctx* p) { clip_free(p); });
+        if (!leader) return nullptr;
+        if (devs.size() > 1) {
+            // devices mode: one replica + one NCCL communicator per GPU, all owned by the leader context
+            leader->replicas.push_back(leader.get());
+            for (size_t i = 1; i < devs.size(); i++) {
+                clip_ctx* r = load_on_device(g, devs[i], 0);
+                if (!r) return nullptr;
+                r->is_replica = true;
+                leader->replicas.push_back(r);
+            }
+            std::vector<DistComm> comms(devs.size());
+            std::string derr;
+            if (!dist_init_all(comms.data(), devs.data(), (int)devs.size(), derr)) { set_err("devices mode: " + derr); return nullptr; }
+            for (size_t i = 0; i < devs.size(); i++) leader->replicas[i]->dist = comms[i];
+            if (verbosity >= 1) printf("%s: devices mode: %zu GPUs, NCCL %d\n", __func__, devs.size(), dist_nccl_version());
+            cudaSetDevice(leader->device);
+        } else if (const char* de = getenv("CLIP_B200_DIST")) {
+            if (!strcmp(de, "env") && getenv("RANK") && getenv("WORLD_SIZE") && atoi(getenv("WORLD_SIZE")) > 1) {
+                if (!clip_b200_dist_init(leader.get(), atoi(getenv("RANK")), atoi(getenv("WORLD_SIZE")), nullptr)) return nullptr;
+            }
+        }
+        return leader.release();
     } catch (const std::exception& e) {
         set_err(std::string("clip_model_load: ") + e.what());
         return nullptr;
@@ -506,13 +613,18 @@ struct clip_ctx* clip_model_load(const char* fname, const int verbosity) {
 
 void clip_free(struct clip_ctx* c) {
     if (!c) return;
+    for (size_t i = 1; i < c->replicas.size(); i++) { c->replicas[i]->is_replica = false; clip_free(c->replicas[i]); }
+    c->replicas.clear();
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    dist_destroy(c->dist);
     preprocess_release(c);
     for (void* p : c->allocs) cudaFree(p);
+    for (int i = 0; i < 2; i++) if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]);
     for (auto& p : c->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) { if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]); if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]); }
+    for (int i = 0; i < 4; i++) if (c->marks[i]) cudaEventDestroy(c->marks[i]);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -641,38 +753,88 @@ bool clip_b200_image_encode_device(const struct clip_ctx* cctx, const void* d_pi
     return sync_and_time(c);
 }
 
-bool clip_image_batch_encode(const struct clip_ctx* cctx, const int n_threads, const struct clip_image_f32_batch* imgs, float* vec,
-                             const bool normalize) {
-    (void)n_threads;
-    clip_ctx* c = const_cast<clip_ctx*>(cctx);
-    if (!c || !c->has_vision) { printf("This gguf file seems to have no vision encoder\n"); return false; }
-    const size_t n = imgs->size;
-    if (n == 0) return true;
+// One GPU: n host images -> embeddings at d_vec (device, may be null) and / or vec (host, may be null).  Host pixels travel on the
+// copy stream, double-buffered against the kernels of the previous micro-batch.  Pinned / registered caller buffers are copied
+// directly; PAGEABLE ones (what clip_image_preprocess returns: new float[]) are first gathered into a pinned arena by host threads,
+// in sub-batches so the H2D of sub-batch k overlaps the memcpy of k+1 -- a pageable cudaMemcpyAsync would be staged synchronously
+// by the driver, one 602 KB image at a time.
+static bool image_batch_encode_one(clip_ctx* c, int n_threads, const clip_image_f32* imgs, size_t n, float* vec, float* d_vec, bool normalize,
+                                   bool sync) {
     Tower& tw = c->vis;
-    for (size_t i = 0; i < n; i++)
-        if (imgs->data[i].nx != tw.image_size || imgs->data[i].ny != tw.image_size || !imgs->data[i].data) { set_err("clip_image_batch_encode: every image must be image_size x image_size"); return false; }
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
-    if (!ensure_ws(c, tw, tw.micro_batch, tw.T, true) || !ensure_out(c, n * tw.proj)) return false;
+    if (!ensure_ws(c, tw, tw.micro_batch, tw.T, true)) return false;
+    if (!d_vec) { if (!ensure_out(c, n * tw.proj)) return false; d_vec = c->d_out; }
     size_t n_chunks, chunk;
     chunking(n, tw.micro_batch, n_chunks, chunk);
     const size_t per = (size_t)tw.image_size * tw.image_size * 3;
+    bool pinned = true;
+    for (size_t i = 0; i < n && pinned; i++) pinned = host_ptr_is_pinned(imgs[i].data);
+    if (!pinned && c->h_stage_cap < (size_t)tw.micro_batch * per) {
+        for (int b = 0; b < 2; b++) {
+            if (c->h_stage[b]) { cudaFreeHost(c->h_stage[b]); c->h_stage[b] = nullptr; }
+            CK(cudaMallocHost((void**)&c->h_stage[b], (size_t)tw.micro_batch * per * 4));
+        }
+        c->h_stage_cap = (size_t)tw.micro_batch * per;
+    }
+    const int nt = std::max(1, std::min({std::max(n_threads, 4), 16, (int)std::thread::hardware_concurrency()}));
     CK(cudaEventRecord(c->ev_t0, c->stream));
     size_t ci = 0;
     for (size_t i0 = 0; i0 < n; i0 += chunk, ci++) {
         const int nb = (int)std::min(chunk, n - i0), b = (int)(ci & 1);
-        // H2D of chunk ci on the copy stream overlaps the kernels of chunk ci-1 (double-buffered staging)
         if (ci >= 2) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
-        for (int j = 0; j < nb; j++)
-            CK(cudaMemcpyAsync(tw.ws.pixels[b] + (size_t)j * per, imgs->data[i0 + j].data, per * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        if (pinned) {
+            for (int j = 0; j < nb; j++)
+                CK(cudaMemcpyAsync(tw.ws.pixels[b] + (size_t)j * per, imgs[i0 + j].data, per * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        } else {
+            if (ci >= 2) CK(cudaEventSynchronize(c->ev_copied[b]));      // the arena's previous H2D has left the host buffer
+            const int sub = 32;
+            for (int j0 = 0; j0 < nb; j0 += sub) {
+                const int ns = std::min(sub, nb - j0);
+                float* dst = c->h_stage[b] + (size_t)j0 * per;
+                const clip_image_f32* src = imgs + i0 + j0;
+                const int t_use = std::min(nt, ns);
+                if (t_use <= 1) { for (int j = 0; j < ns; j++) memcpy(dst + (size_t)j * per, src[j].data, per * 4); }
+                else {
+                    std::vector<std::thread> th;
+                    for (int t = 0; t < t_use; t++)
+                        th.emplace_back([=]() { for (int j = t; j < ns; j += t_use) memcpy(dst + (size_t)j * per, src[j].data, per * 4); });
+                    for (auto& t : th) t.join();
+                }
+                CK(cudaMemcpyAsync(tw.ws.pixels[b] + (size_t)j0 * per, dst, (size_t)ns * per * 4, cudaMemcpyHostToDevice, c->copy_stream));
+            }
+        }
         CK(cudaEventRecord(c->ev_copied[b], c->copy_stream));
         CK(cudaStreamWaitEvent(c->stream, c->ev_copied[b], 0));
-        if (!vision_forward(c, tw.ws.pixels[b], nb, c->d_out + i0 * tw.proj, normalize)) return false;
+        if (!vision_forward(c, tw.ws.pixels[b], nb, d_vec + i0 * tw.proj, normalize)) return false;
         CK(cudaEventRecord(c->ev_consumed[b], c->stream));
     }
     CK(cudaEventRecord(c->ev_t1, c->stream));
-    CK(cudaMemcpyAsync(vec, c->d_out, n * tw.proj * 4, cudaMemcpyDeviceToHost, c->stream));
-    return sync_and_time(c);
+    if (vec) CK(cudaMemcpyAsync(vec, d_vec, n * tw.proj * 4, cudaMemcpyDeviceToHost, c->stream));
+    return sync ? sync_and_time(c) : true;
+}
+
+static bool check_images(clip_ctx* c, const clip_image_f32* imgs, size_t n, const char* who) {
+    for (size_t i = 0; i < n; i++)
+        if (imgs[i].nx != c->vis.image_size || imgs[i].ny != c->vis.image_size || !imgs[i].data) { set_err(std::string(who) + ": every image must be image_size x image_size"); return false; }
+    return true;
+}
+
+bool clip_image_batch_encode(const struct clip_ctx* cctx, const int n_threads, const struct clip_image_f32_batch* imgs, float* vec,
+                             const bool normalize) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || !c->has_vision) { printf("This gguf file seems to have no vision encoder\n"); return false; }
+    const size_t n = imgs->size;
+    if (n == 0) return true;
+    if (!check_images(c, imgs->data, n, "clip_image_batch_encode")) return false;
+    if (c->replicas.size() > 1 && n >= c->replicas.size()) {
+        // devices mode: contiguous shards, every GPU copies its slice of the result straight into the caller's vec (no exchange needed)
+        const int d = c->vis.proj;
+        return for_each_replica(c, n, [&](clip_ctx* r, int, size_t lo, size_t hi) {
+            return hi == lo || image_batch_encode_one(r, n_threads, imgs->data + lo, hi - lo, vec + lo * d, nullptr, normalize, true);
+        });
+    }
+    return image_batch_encode_one(c, n_threads, imgs->data, n, vec, nullptr, normalize, true);
 }
 
 bool clip_image_encode(const struct clip_ctx* ctx, const int n_threads, struct clip_image_f32* img, float* vec, const bool normalize) {
@@ -682,8 +844,9 @@ bool clip_image_encode(const struct clip_ctx* ctx, const int n_threads, struct c
     return clip_image_batch_encode(ctx, n_threads, &b, vec, normalize);
 }
 
+// n sequences padded to T tokens on the host (h_ids / h_last) or on the device (d_ids / d_lens) -> d_out_dev (device) and / or vec_host
 static bool text_encode_impl(clip_ctx* c, const int32_t* h_ids, const int32_t* h_last, const int32_t* d_ids, const int32_t* d_lens,
-                             size_t n, int T, float* vec_host, float* vec_dev, bool normalize) {
+                             size_t n, int T, float* vec_host, float* vec_dev, bool normalize, bool sync = true) {
     Tower& tw = c->txt;
     // the padded length is fixed per context so that one workspace serves every call
     if (T > tw.n_ctx) { set_err("sequence longer than context_length"); return false; }
@@ -700,13 +863,43 @@ static bool text_encode_impl(clip_ctx* c, const int32_t* h_ids, const int32_t* h
             CK(cudaMemcpyAsync(tw.ws.last, h_last + i0, (size_t)nb * 4, cudaMemcpyHostToDevice, c->stream));
         } else {
             CK(cudaMemcpyAsync(tw.ws.ids, d_ids + i0 * T, (size_t)nb * T * 4, cudaMemcpyDeviceToDevice, c->stream));
-            CK(cudaMemcpyAsync(tw.ws.last, d_lens + i0, (size_t)nb * 4, cudaMemcpyDeviceToDevice, c->stream));   // already len-1
+            launch_fill_last(d_lens ? d_lens + i0 : nullptr, tw.ws.last, nb, T, c->stream);
         }
         if (!text_forward(c, nb, T, d_out + i0 * tw.proj, normalize)) return false;
     }
     CK(cudaEventRecord(c->ev_t1, c->stream));
     if (vec_host) CK(cudaMemcpyAsync(vec_host, d_out, n * tw.proj * 4, cudaMemcpyDeviceToHost, c->stream));
-    return sync_and_time(c);
+    return sync ? sync_and_time(c) : true;
+}
+
+// host token sequences -> padded id matrix + EOT row indices.  Padding to a multiple of 8 tokens is causally invisible to the EOT row.
+static bool pack_tokens(clip_ctx* c, const clip_tokens* seqs, size_t n, std::vector<int32_t>& ids, std::vector<int32_t>& last, int& T_out) {
+    size_t T = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (seqs[i].size == 0 || !seqs[i].data) { set_err("empty token sequence"); return false; }
+        T = std::max(T, seqs[i].size);
+    }
+    if ((int)T > c->txt.n_ctx) { set_err("token sequence longer than context_length (" + std::to_string(c->txt.n_ctx) + ")"); return false; }
+    T = std::min<size_t>((T + 7) / 8 * 8, (size_t)c->txt.n_ctx);
+    ids.assign(n * T, 0);
+    last.resize(n);
+    for (size_t i = 0; i < n; i++) {
+        memcpy(ids.data() + i * T, seqs[i].data, seqs[i].size * 4);
+        last[i] = (int32_t)seqs[i].size - 1;     // the reference selects row N-1 (clip.cpp:1154-1155)
+    }
+    T_out = (int)T;
+    return true;
+}
+
+static bool text_batch_encode_one(clip_ctx* c, const clip_tokens* seqs, size_t n, float* vec, float* d_vec, bool normalize, bool sync) {
+    std::vector<int32_t> ids, last;
+    int T = 0;
+    if (!pack_tokens(c, seqs, n, ids, last, T)) return false;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    // ids / last are pageable vectors: the async copies inside return only after the driver has staged them, so they may go out of
+    // scope when this function returns even with sync == false
+    return text_encode_impl(c, ids.data(), last.data(), nullptr, nullptr, n, T, vec, d_vec, normalize, sync);
 }
 
 bool clip_text_batch_encode(const struct clip_ctx* cctx, const int n_threads, const struct clip_tokens* seqs, const size_t n, float* vec,
@@ -715,22 +908,13 @@ bool clip_text_batch_encode(const struct clip_ctx* cctx, const int n_threads, co
     clip_ctx* c = const_cast<clip_ctx*>(cctx);
     if (!c || !c->has_text) { printf("This GGUF file seems to have no text encoder\n"); return false; }
     if (n == 0) return true;
-    size_t T = 0;
-    for (size_t i = 0; i < n; i++) {
-        if (seqs[i].size == 0 || !seqs[i].data) { set_err("empty token sequence"); return false; }
-        T = std::max(T, seqs[i].size);
+    if (c->replicas.size() > 1 && n >= 8 * c->replicas.size()) {
+        const int d = c->txt.proj;
+        return for_each_replica(c, n, [&](clip_ctx* r, int, size_t lo, size_t hi) {
+            return hi == lo || text_batch_encode_one(r, seqs + lo, hi - lo, vec + lo * d, nullptr, normalize, true);
+        });
     }
-    if ((int)T > c->txt.n_ctx) { set_err("token sequence longer than context_length (" + std::to_string(c->txt.n_ctx) + ")"); return false; }
-    // pad to a multiple of 8 tokens (cheap) -- padded positions are causally invisible to the EOT row
-    T = std::min<size_t>((T + 7) / 8 * 8, (size_t)c->txt.n_ctx);
-    std::vector<int32_t> ids(n * T, 0), last(n);
-    for (size_t i = 0; i < n; i++) {
-        memcpy(ids.data() + i * T, seqs[i].data, seqs[i].size * 4);
-        last[i] = (int32_t)seqs[i].size - 1;     // the reference selects row N-1 (clip.cpp:1154-1155)
-    }
-    std::lock_guard<std::mutex> lk(c->mu);
-    CK(cudaSetDevice(c->device));
-    return text_encode_impl(c, ids.data(), last.data(), nullptr, nullptr, n, (int)T, vec, nullptr, normalize);
+    return text_batch_encode_one(c, seqs, n, vec, nullptr, normalize, true);
 }
 
 bool clip_text_encode(const struct clip_ctx* ctx, const int n_threads, const struct clip_tokens* tokens, float* vec, const bool normalize) {
@@ -743,20 +927,12 @@ bool clip_b200_text_encode_device(const struct clip_ctx* cctx, const void* d_ids
     clip_ctx* c = const_cast<clip_ctx*>(cctx);
     if (!c || !c->has_text) { set_err("no text encoder"); return false; }
     if (n == 0) return true;
+    if (seq_len < 1 || seq_len > c->txt.n_ctx) { set_err("clip_b200_text_encode_device: seq_len must be in [1, context_length]"); return false; }
+    if (!d_ids || !d_vec) { set_err("clip_b200_text_encode_device: null device pointer"); return false; }
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
-    // device lengths are converted to last-row indices on the host side of this call (tiny D2H)
-    std::vector<int32_t> last(n, seq_len - 1);
-    if (d_lens) {
-        CK(cudaMemcpy(last.data(), d_lens, n * 4, cudaMemcpyDeviceToHost));
-        for (auto& v : last) { if (v < 1 || v > seq_len) { set_err("bad sequence length"); return false; } v -= 1; }
-    }
-    int32_t* d_last = nullptr;
-    CK(cudaMalloc(&d_last, n * 4));
-    cudaError_t e = cudaMemcpy(d_last, last.data(), n * 4, cudaMemcpyHostToDevice);
-    bool ok = e == cudaSuccess && text_encode_impl(c, nullptr, nullptr, (const int32_t*)d_ids, d_last, n, seq_len, nullptr, (float*)d_vec, normalize);
-    cudaFree(d_last);
-    return ok;
+    // lengths stay on the device: a tiny kernel turns them into EOT-row indices per micro-batch (clamped to [1, seq_len])
+    return text_encode_impl(c, nullptr, nullptr, (const int32_t*)d_ids, (const int32_t*)d_lens, n, seq_len, nullptr, (float*)d_vec, normalize);
 }
 
 float clip_similarity_score(const float* vec1, const float* vec2, const int vec_dim) {
@@ -815,31 +991,318 @@ bool clip_zero_shot_label_image(struct clip_ctx* ctx, const int n_threads, const
     return softmax_with_sorting(sims.data(), (int)n_labels, scores, indices);
 }
 
+// =====================================================================================================================
+// Scoring on the device (search.cu): similarity matrix -> [softmax_with_sorting arithmetic] -> top-k, results to the host
+// =====================================================================================================================
+// d_q [nq, d] x d_db [ndb, d] -> host scores / indices [nq, k], best first (ties: lower index first).  softmax: p = (exp(s)+1e-9)/sum
+// over the whole row first (clip.cpp:1591-1622); otherwise the raw dot products are ranked (nearest-neighbour search).
+// The stream is synchronised on return.  Caller holds c->mu and has set the device.
+static bool score_topk_locked(clip_ctx* c, const float* d_q, size_t nq, const float* d_db, size_t ndb, int d, int k, bool softmax,
+                              float* scores, int* indices) {
+    if (nq == 0 || ndb == 0) return true;
+    if (ndb > 0x7fffffffull || nq > 0x7fffffffull) { set_err("scoring: more than 2^31 rows"); return false; }
+    if (k <= 0 || (size_t)k > ndb) k = (int)ndb;
+    const int SL = topk_slice();
+    const size_t budget = (size_t)32 << 20;                               // floats of similarity scratch per pass (128 MB)
+    size_t CH = std::min(ndb, std::max<size_t>(budget / std::min<size_t>(nq, 256), (size_t)SL));
+    if (softmax) CH = ndb;                                                // the normalisation needs whole rows
+    const size_t RB = std::max<size_t>(1, std::min<size_t>({nq, budget / CH + 1, (size_t)32768}));
+    size_t nsl = 0;
+    for (size_t c0 = 0; c0 < ndb; c0 += CH) nsl += (std::min(CH, ndb - c0) + SL - 1) / SL;
+    const int kk = std::min(k, SL);
+    const bool device_select = nsl == 1 || k <= 1024;                    // each stage must shrink the candidate set
+    if (!ensure_buf(c, &c->d_logits, &c->d_logits_cap, RB * CH)) return false;
+    const size_t cand_ld = nsl * (size_t)kk;
+    if (device_select) {
+        size_t cap0 = c->d_cand_cap, cap1 = c->d_cand_cap, cap2 = c->d_cand_cap, cap3 = c->d_cand_cap;
+        if (!ensure_buf(c, &c->d_cand_v[0], &cap0, RB * cand_ld) || !ensure_buf(c, &c->d_cand_v[1], &cap1, RB * cand_ld) ||
+            !ensure_buf(c, &c->d_cand_i[0], &cap2, RB * cand_ld) || !ensure_buf(c, &c->d_cand_i[1], &cap3, RB * cand_ld)) return false;
+        c->d_cand_cap = std::min(std::min(cap0, cap1), std::min(cap2, cap3));
+    }
+    std::vector<float> hrow;
+    std::vector<int> hidx;
+    for (size_t r0 = 0; r0 < nq; r0 += RB) {
+        const int rows = (int)std::min(RB, nq - r0);
+        size_t sl0 = 0;
+        for (size_t c0 = 0; c0 < ndb; c0 += CH) {
+            const int cols = (int)std::min(CH, ndb - c0);
+            { Scope s(c, K_OTHER); launch_similarity(d_q + r0 * d, d_db + c0 * d, c->d_logits, rows, cols, d, CH, c->stream); }
+            if (softmax) { Scope s(c, K_OTHER); launch_softmax_ref(c->d_logits, rows, cols, CH, c->stream); }
+            if (device_select) {
+                Scope s(c, K_OTHER);
+                launch_topk_stage(c->d_logits, nullptr, CH, rows, cols, (int)c0, kk, c->d_cand_v[0], c->d_cand_i[0], cand_ld, (int)(sl0 * kk), c->stream);
+                sl0 += ((size_t)cols + SL - 1) / SL;
+            } else {
+                // full ranking of rows longer than one sort slice (top_k > 1024): ranked on the host, as the reference does
+                hrow.resize((size_t)rows * cols);
+                CK(cudaMemcpy2DAsync(hrow.data(), (size_t)cols * 4, c->d_logits, CH * 4, (size_t)cols * 4, rows, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaStreamSynchronize(c->stream));
+                hidx.resize(cols);
+                for (int i = 0; i < rows; i++) {
+                    const float* r = hrow.data() + (size_t)i * cols;
+                    std::iota(hidx.begin(), hidx.end(), 0);
+                    std::partial_sort(hidx.begin(), hidx.begin() + k, hidx.end(), [&](int a, int b) { return r[a] > r[b] || (r[a] == r[b] && a < b); });
+                    for (int j = 0; j < k; j++) { scores[(r0 + i) * k + j] = r[hidx[j]]; indices[(r0 + i) * k + j] = hidx[j]; }
+                }
+            }
+        }
+        if (!device_select) continue;
+        int cur = 0;
+        size_t cur_n = cand_ld;
+        while (cur_n > (size_t)SL || (cur_n > (size_t)kk && nsl > 1)) {      // merge stages: candidates of all slices compete again
+            const size_t nslices = (cur_n + SL - 1) / SL;
+            { Scope s(c, K_OTHER); launch_topk_stage(c->d_cand_v[cur], c->d_cand_i[cur], cand_ld, rows, (int)cur_n, 0, kk, c->d_cand_v[cur ^ 1], c->d_cand_i[cur ^ 1], cand_ld, 0, c->stream); }
+            cur ^= 1;
+            cur_n = nslices * (size_t)kk;
+            if (nslices == 1) break;
+        }
+        CK(cudaMemcpy2DAsync(scores + r0 * k, (size_t)k * 4, c->d_cand_v[cur], cand_ld * 4, (size_t)k * 4, rows, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpy2DAsync(indices + r0 * k, (size_t)k * 4, c->d_cand_i[cur], cand_ld * 4, (size_t)k * 4, rows, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    CK(cudaGetLastError());
+    return true;
+}
+
 bool clip_b200_zero_shot_batch(const struct clip_ctx* cctx, const void* d_img, size_t n_img, const void* d_txt, size_t n_txt, float* scores,
                                int* indices, int top_k) {
     clip_ctx* c = const_cast<clip_ctx*>(cctx);
     if (!c) return false;
-    if (top_k <= 0 || (size_t)top_k > n_txt) top_k = (int)n_txt;
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     const int d = c->has_vision ? c->vhp.projection_dim : c->thp.projection_dim;
-    float* d_logits = nullptr;
-    CK(cudaMalloc(&d_logits, n_img * n_txt * 4));
-    { Scope s(c, K_OTHER); launch_logits((const float*)d_img, (const float*)d_txt, d_logits, (int)n_img, (int)n_txt, d, c->stream); }
-    { Scope s(c, K_OTHER); launch_softmax_plain(d_logits, (int)n_img, (int)n_txt, c->stream); }
-    std::vector<float> p(n_img * n_txt);
-    cudaError_t e = cudaMemcpyAsync(p.data(), d_logits, p.size() * 4, cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(d_logits);
-    if (e != cudaSuccess) { set_err(std::string("zero_shot_batch failed: ") + cudaGetErrorString(e)); return false; }
-    std::vector<int> idx(n_txt);
-    for (size_t i = 0; i < n_img; i++) {
-        const float* r = p.data() + i * n_txt;
-        std::iota(idx.begin(), idx.end(), 0);
-        std::partial_sort(idx.begin(), idx.begin() + top_k, idx.end(), [&](int a, int b) { return r[a] > r[b] || (r[a] == r[b] && a < b); });
-        for (int k = 0; k < top_k; k++) { scores[i * top_k + k] = r[idx[k]]; indices[i * top_k + k] = idx[k]; }
-    }
+    return score_topk_locked(c, (const float*)d_img, n_img, (const float*)d_txt, n_txt, d, top_k, true, scores, indices);
+}
+
+bool clip_b200_topk_search(const struct clip_ctx* cctx, const void* d_queries, size_t n_queries, const void* d_db, size_t n_db, int top_k,
+                           float* scores, int* indices) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c) return false;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const int d = c->has_vision ? c->vhp.projection_dim : c->thp.projection_dim;
+    return score_topk_locked(c, (const float*)d_queries, n_queries, (const float*)d_db, n_db, d, top_k, false, scores, indices);
+}
+
+// =====================================================================================================================
+// Multi-GPU inside the library (dist.h).  ranks mode: one process per GPU joined by clip_b200_dist_init; devices mode: one
+// process, CLIP_B200_DEVICES at clip_model_load.  The ONLY exchange of the path is one NCCL all-gather of final embeddings.
+// =====================================================================================================================
+bool clip_b200_dist_unique_id(void* out128) {
+    std::string e;
+    if (!dist_unique_id(out128, e)) { set_err(e); return false; }
     return true;
+}
+
+bool clip_b200_dist_init_with_id(struct clip_ctx* c, int rank, int world, const void* id128) {
+    if (!c || !id128) { set_err("clip_b200_dist_init: null argument"); return false; }
+    if (c->replicas.size() > 1) { set_err("clip_b200_dist_init: this context is already in devices mode (CLIP_B200_DEVICES)"); return false; }
+    if (c->dist.comm) { set_err("clip_b200_dist_init: already initialised"); return false; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    std::string e;
+    if (!dist_init_rank(c->dist, rank, world, id128, e)) { set_err(e); return false; }
+    return true;
+}
+
+bool clip_b200_dist_init(struct clip_ctx* c, int rank, int world, const char* rendezvous) {
+    if (!c) { set_err("clip_b200_dist_init: null context"); return false; }
+    if (world == 1) return true;
+    unsigned char id[128];
+    std::string e;
+    if (!dist_rendezvous_id(rank, world, rendezvous, id, e)) { set_err(e); return false; }
+    return clip_b200_dist_init_with_id(c, rank, world, id);
+}
+
+int clip_b200_dist_rank(const struct clip_ctx* c) { return c ? c->dist.rank : 0; }
+int clip_b200_dist_world(const struct clip_ctx* c) { return c ? (c->replicas.size() > 1 ? 1 : c->dist.world) : 1; }
+int clip_b200_device_count(const struct clip_ctx* c) { return c ? std::max<int>(1, (int)c->replicas.size()) : 0; }
+int clip_b200_nccl_version(void) { return dist_nccl_version(); }
+int clip_b200_cuda_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; } return n; }
+
+static bool ranks_mode(const clip_ctx* c) { return c->replicas.size() <= 1 && c->dist.comm && c->dist.world > 1; }
+
+static bool ensure_scalars(clip_ctx* c) {
+    if (c->d_scalars) return true;
+    return dev_alloc(c, &c->d_scalars, 16);
+}
+
+bool clip_b200_dist_all_gather(const struct clip_ctx* cctx, const void* d_send, void* d_recv, size_t bytes_per_rank) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c) return false;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    if (!ranks_mode(c)) {
+        if (d_send != d_recv) CK(cudaMemcpyAsync(d_recv, d_send, bytes_per_rank, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        std::string e;
+        if (!dist_all_gather(c->dist, d_send, d_recv, bytes_per_rank, c->stream, e)) { set_err(e); return false; }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return true;
+}
+
+bool clip_b200_dist_max_f64(const struct clip_ctx* cctx, double* vals, int n) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || n < 0 || n > 16) { set_err("clip_b200_dist_max_f64: n must be in [0, 16]"); return false; }
+    if (!ranks_mode(c) || n == 0) return true;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    if (!ensure_scalars(c)) return false;
+    CK(cudaMemcpyAsync(c->d_scalars, vals, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    std::string e;
+    if (!dist_all_reduce_max_f64(c->dist, c->d_scalars, (size_t)n, c->stream, e)) { set_err(e); return false; }
+    CK(cudaMemcpyAsync(vals, c->d_scalars, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return true;
+}
+
+bool clip_b200_dist_barrier(const struct clip_ctx* cctx) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c) return false;
+    if (ranks_mode(c)) { double v = 0.0; if (!clip_b200_dist_max_f64(c, &v, 1)) return false; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    return true;
+}
+
+// ranks mode: every rank encodes ITS n_local items and ends with ALL world * n_local embeddings, rank-major.  The last kernel of
+// the tower (K5 l2norm) writes straight into this rank's slot of the gather buffer; the all-gather runs in place on the launch stream.
+static bool gather_in_place(clip_ctx* c, float* d_all, size_t n_local, int d) {
+    if (!ranks_mode(c)) return true;
+    std::string e;
+    const size_t bytes = n_local * (size_t)d * 4;
+    if (!dist_all_gather(c->dist, (const char*)d_all + (size_t)c->dist.rank * bytes, d_all, bytes, c->stream, e)) { set_err(e); return false; }
+    return true;
+}
+
+bool clip_b200_image_encode_device_all(const struct clip_ctx* cctx, const void* d_pixels, size_t n_local, void* d_vec_all, bool normalize) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || !c->has_vision) { set_err("no vision encoder"); return false; }
+    if (n_local == 0) return true;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const int d = c->vis.proj;
+    float* slot = (float*)d_vec_all + (ranks_mode(c) ? (size_t)c->dist.rank * n_local * d : 0);
+    if (!image_encode_device_locked(c, (const float*)d_pixels, n_local, slot, normalize)) return false;
+    if (!gather_in_place(c, (float*)d_vec_all, n_local, d)) return false;
+    CK(cudaEventRecord(c->ev_t1, c->stream));
+    return sync_and_time(c);
+}
+
+bool clip_b200_image_batch_encode_all(const struct clip_ctx* cctx, const int n_threads, const struct clip_image_f32_batch* imgs, float* vec_all,
+                                      const bool normalize) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || !c->has_vision) { set_err("no vision encoder"); return false; }
+    if (!ranks_mode(c)) return clip_image_batch_encode(c, n_threads, imgs, vec_all, normalize);
+    const size_t n = imgs->size;
+    if (n == 0) { set_err("clip_b200_image_batch_encode_all: every rank must pass the same, non-zero number of images"); return false; }
+    if (!check_images(c, imgs->data, n, "clip_b200_image_batch_encode_all")) return false;
+    const int d = c->vis.proj, w = c->dist.world;
+    { std::lock_guard<std::mutex> lk(c->mu); CK(cudaSetDevice(c->device)); if (!ensure_out(c, (size_t)w * n * d)) return false; }
+    if (!image_batch_encode_one(c, n_threads, imgs->data, n, nullptr, c->d_out + (size_t)c->dist.rank * n * d, normalize, false)) return false;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!gather_in_place(c, c->d_out, n, d)) return false;
+    CK(cudaEventRecord(c->ev_t1, c->stream));
+    CK(cudaMemcpyAsync(vec_all, c->d_out, (size_t)w * n * d * 4, cudaMemcpyDeviceToHost, c->stream));
+    return sync_and_time(c);
+}
+
+bool clip_b200_text_batch_encode_all(const struct clip_ctx* cctx, const int n_threads, const struct clip_tokens* seqs, const size_t n, float* vec_all,
+                                     const bool normalize) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || !c->has_text) { set_err("no text encoder"); return false; }
+    if (!ranks_mode(c)) return clip_text_batch_encode(c, n_threads, seqs, n, vec_all, normalize);
+    if (n == 0) { set_err("clip_b200_text_batch_encode_all: every rank must pass the same, non-zero number of sequences"); return false; }
+    const int d = c->txt.proj, w = c->dist.world;
+    { std::lock_guard<std::mutex> lk(c->mu); CK(cudaSetDevice(c->device)); if (!ensure_out(c, (size_t)w * n * d)) return false; }
+    if (!text_batch_encode_one(c, seqs, n, nullptr, c->d_out + (size_t)c->dist.rank * n * d, normalize, false)) return false;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!gather_in_place(c, c->d_out, n, d)) return false;
+    CK(cudaEventRecord(c->ev_t1, c->stream));
+    CK(cudaMemcpyAsync(vec_all, c->d_out, (size_t)w * n * d * 4, cudaMemcpyDeviceToHost, c->stream));
+    return sync_and_time(c);
+}
+
+bool clip_b200_text_encode_device_all(const struct clip_ctx* cctx, const void* d_ids, const void* d_lens, size_t n_local, int seq_len,
+                                      void* d_vec_all, bool normalize) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || !c->has_text) { set_err("no text encoder"); return false; }
+    if (n_local == 0) return true;
+    if (seq_len < 1 || seq_len > c->txt.n_ctx || !d_ids || !d_vec_all) { set_err("clip_b200_text_encode_device_all: bad arguments"); return false; }
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    const int d = c->txt.proj;
+    float* slot = (float*)d_vec_all + (ranks_mode(c) ? (size_t)c->dist.rank * n_local * d : 0);
+    if (!text_encode_impl(c, nullptr, nullptr, (const int32_t*)d_ids, (const int32_t*)d_lens, n_local, seq_len, nullptr, slot, normalize, false)) return false;
+    if (!gather_in_place(c, (float*)d_vec_all, n_local, d)) return false;
+    CK(cudaEventRecord(c->ev_t1, c->stream));
+    return sync_and_time(c);
+}
+
+// Batched zero-shot labelling (BASELINE.json configs[4]; per image the arithmetic of clip_zero_shot_label_image, clip.cpp:1624-1659):
+//   single GPU   : n images x n_labels labels
+//   devices mode : images AND labels are sharded over the GPUs, the label embeddings are all-gathered (NCCL), every GPU scores its images
+//   ranks mode   : the caller passes THIS rank's images and THIS rank's label shard (same count on every rank); label j of rank r has
+//                  global index r * n_labels + j; scores / indices cover this rank's images against all world * n_labels labels
+// scores / indices: [n images, top_k], best first.  The embeddings never leave the GPUs.
+bool clip_b200_zero_shot_images(const struct clip_ctx* cctx, const int n_threads, const struct clip_image_f32_batch* imgs,
+                                const struct clip_tokens* labels, const size_t n_labels, const bool normalize, int top_k, float* scores,
+                                int* indices) {
+    clip_ctx* c = const_cast<clip_ctx*>(cctx);
+    if (!c || !(c->has_text && c->has_vision)) { set_err("clip_b200_zero_shot_images needs a two-tower model"); return false; }
+    const size_t n = imgs ? imgs->size : 0;
+    if (n == 0 || n_labels == 0) return n == 0;
+    if (!check_images(c, imgs->data, n, "clip_b200_zero_shot_images")) return false;
+    const int d = c->vis.proj;
+    if (c->replicas.size() > 1) {
+        const int w = (int)c->replicas.size();
+        const size_t per = (n_labels + w - 1) / w, tot = (size_t)w * per;      // equal slots; only the last ones may be partly empty
+        if (top_k <= 0 || (size_t)top_k > n_labels) top_k = (int)n_labels;
+        // phase 1: every GPU encodes its image shard and its label shard (slot r of its own gather buffer)
+        if (!for_each_replica(c, n, [&](clip_ctx* r, int ri, size_t lo, size_t hi) {
+                {
+                    std::lock_guard<std::mutex> lk(r->mu);
+                    CK(cudaSetDevice(r->device));
+                    if (!ensure_buf(r, &r->d_emb[0], &r->d_emb_cap[0], std::max<size_t>(hi - lo, 1) * d) || !ensure_buf(r, &r->d_emb[1], &r->d_emb_cap[1], tot * d)) return false;
+                    CK(cudaMemsetAsync(r->d_emb[1], 0, tot * d * 4, r->stream));
+                }
+                if (hi > lo && !image_batch_encode_one(r, n_threads, imgs->data + lo, hi - lo, nullptr, r->d_emb[0], normalize, false)) return false;
+                const size_t l0 = std::min(n_labels, (size_t)ri * per), l1 = std::min(n_labels, l0 + per);
+                if (l1 > l0 && !text_batch_encode_one(r, labels + l0, l1 - l0, nullptr, r->d_emb[1] + (size_t)ri * per * d, normalize, false)) return false;
+                return true;
+            })) return false;
+        // phase 2: ONE all-gather of the label embeddings, in place on every GPU (group call: one thread drives all communicators)
+        std::string e;
+        if (!dist_group_start(e)) { set_err(e); return false; }
+        for (int ri = 0; ri < w; ri++) {
+            clip_ctx* r = c->replicas[ri];
+            cudaSetDevice(r->device);
+            if (!dist_all_gather(r->dist, r->d_emb[1] + (size_t)ri * per * d, r->d_emb[1], per * d * 4, r->stream, e)) { dist_group_end(e); set_err(e); return false; }
+        }
+        if (!dist_group_end(e)) { set_err(e); return false; }
+        cudaSetDevice(c->device);
+        // phase 3: every GPU ranks the labels for its images and copies its slice of the result to the caller
+        return for_each_replica(c, n, [&](clip_ctx* r, int, size_t lo, size_t hi) {
+            if (hi == lo) return true;
+            std::lock_guard<std::mutex> lk(r->mu);
+            CK(cudaSetDevice(r->device));
+            return score_topk_locked(r, r->d_emb[0], hi - lo, r->d_emb[1], n_labels, d, top_k, true, scores + lo * top_k, indices + lo * top_k);
+        });
+    }
+    const int w = ranks_mode(c) ? c->dist.world : 1, rank = ranks_mode(c) ? c->dist.rank : 0;
+    const size_t n_all = (size_t)w * n_labels;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        CK(cudaSetDevice(c->device));
+        if (!ensure_buf(c, &c->d_emb[0], &c->d_emb_cap[0], n * d) || !ensure_buf(c, &c->d_emb[1], &c->d_emb_cap[1], n_all * d)) return false;
+    }
+    if (!image_batch_encode_one(c, n_threads, imgs->data, n, nullptr, c->d_emb[0], normalize, false)) return false;
+    if (!text_batch_encode_one(c, labels, n_labels, nullptr, c->d_emb[1] + (size_t)rank * n_labels * d, normalize, false)) return false;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(cudaSetDevice(c->device));
+    if (!gather_in_place(c, c->d_emb[1], n_labels, d)) return false;
+    return score_topk_locked(c, c->d_emb[0], n, c->d_emb[1], n_all, d, top_k, true, scores, indices);
 }
 
 bool clip_model_quantize(const char* fname_inp, const char* fname_out, const int itype) {
@@ -878,21 +1341,22 @@ void clip_b200_set_micro_batch(const struct clip_ctx* cc, int images, int sequen
     if (images > 0 && c->has_vision && c->vis.ws.cap_items == 0) c->vis.micro_batch = images;
     if (sequences > 0 && c->has_text && c->txt.ws.cap_items == 0) c->txt.micro_batch = sequences;
 }
-// CUDA-event stopwatch on the launch stream (slots 0..3) so that callers can time a region on the device
-static cudaEvent_t g_marks[4] = {nullptr, nullptr, nullptr, nullptr};
-bool clip_b200_mark(const struct clip_ctx* c, int slot) {
+// CUDA-event stopwatch on the launch stream (slots 0..3) so that callers can time a region on the device; the events belong to
+// the context (= to its device)
+bool clip_b200_mark(const struct clip_ctx* cc, int slot) {
+    clip_ctx* c = const_cast<clip_ctx*>(cc);
     if (!c || slot < 0 || slot > 3) return false;
-    cudaSetDevice(c->device);
-    if (!g_marks[slot]) CK(cudaEventCreate(&g_marks[slot]));
-    CK(cudaEventRecord(g_marks[slot], c->stream));
+    CK(cudaSetDevice(c->device));
+    if (!c->marks[slot]) CK(cudaEventCreate(&c->marks[slot]));
+    CK(cudaEventRecord(c->marks[slot], c->stream));
     return true;
 }
 float clip_b200_mark_elapsed_ms(const struct clip_ctx* c, int a, int b) {
-    if (!c || a < 0 || a > 3 || b < 0 || b > 3 || !g_marks[a] || !g_marks[b]) return -1.f;
+    if (!c || a < 0 || a > 3 || b < 0 || b > 3 || !c->marks[a] || !c->marks[b]) return -1.f;
     cudaSetDevice(c->device);
-    if (cudaEventSynchronize(g_marks[b]) != cudaSuccess) return -1.f;
+    if (cudaEventSynchronize(c->marks[b]) != cudaSuccess) return -1.f;
     float ms = -1.f;
-    cudaEventElapsedTime(&ms, g_marks[a], g_marks[b]);
+    cudaEventElapsedTime(&ms, c->marks[a], c->marks[b]);
     return ms;
 }
 uint64_t clip_b200_kernel_launches(const struct clip_ctx* c) { return c ? c->launches : 0; }
@@ -923,9 +1387,12 @@ int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int e
                          const float* bias, const float* resid_in, float* y_out, float* ms) {
     g_err.clear();
     if (gemm_init() != cudaSuccess) { set_err("gemm_init failed"); return 1; }
+    (void)resid_in;      // kept in the signature for ABI stability: the read-modify-write epilogue it fed is gone
+    int dev = 0;
+    cudaGetDevice(&dev);
     cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, 0);
-    const bool out32 = (epi == EPI_RESID32 || epi == EPI_STORE32);
+    cudaGetDeviceProperties(&prop, dev);
+    const bool out32 = (epi == EPI_STORE32);
     int eff_q = qtype;
     std::vector<uint16_t> x16((size_t)M * K);
     for (size_t i = 0; i < x16.size(); i++) x16[i] = operand_bf16 ? f32_to_bf16(x[i]) : f32_to_f16(x[i]);
@@ -961,8 +1428,7 @@ int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int e
         if (eff_q == QT_F16) d_w = d_raw;
         else { if ((e = cudaMalloc(&d_w, wdev.size())) != cudaSuccess) { fail("malloc w", e); break; } cudaMemcpy(d_w, wdev.data(), wdev.size(), cudaMemcpyHostToDevice); }
         if (bias) { cudaMalloc(&d_bias, (size_t)N * 4); cudaMemcpy(d_bias, bias, (size_t)N * 4, cudaMemcpyHostToDevice); }
-        if (epi == EPI_RESID32 && resid_in) cudaMemcpy(d_out, resid_in, out_bytes, cudaMemcpyHostToDevice);
-        else cudaMemset(d_out, 0, out_bytes);
+        cudaMemset(d_out, 0, out_bytes);
         TmaMap xm, xh, wm;
         memset(&wm, 0, sizeof(wm));
         if (!make_tma_2d_16bit(&xm, d_x, M, K, K, GEMM_BN) || !make_tma_2d_16bit(&xh, d_x, M, K, K, GEMM_BN / 2)) { set_err("tensor map X failed"); rc = 4; break; }
@@ -1004,8 +1470,10 @@ int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int caus
     g_err.clear();
     if (attention_tc_init() != cudaSuccess) { set_err("attention_tc_init failed"); return 1; }
     if (!use_legacy && !attention_tc_supported(T)) { set_err("T not supported by the tcgen05 attention kernel"); return 2; }
+    int dev = 0;
+    cudaGetDevice(&dev);
     cudaDeviceProp prop;
-    cudaGetDeviceProperties(&prop, 0);
+    cudaGetDeviceProperties(&prop, dev);
     const size_t rows = (size_t)nseq * T, hid = (size_t)H * 64;
     std::vector<uint16_t> h16(rows * 3 * hid);
     for (size_t i = 0; i < h16.size(); i++) h16[i] = operand_bf16 ? f32_to_bf16(qkv[i]) : f32_to_f16(qkv[i]);
@@ -1017,7 +1485,9 @@ int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int caus
         cudaError_t e;
         // pad by one 272-row box: the K/V boxes of the last sequence read (and discard) rows past the end
         if ((e = cudaMalloc(&d_qkv, (rows + 272) * 3 * hid * 2)) != cudaSuccess || (e = cudaMalloc(&d_out, rows * hid * 2)) != cudaSuccess) { set_err(std::string("cudaMalloc: ") + cudaGetErrorString(e)); rc = 3; break; }
-        cudaMemset(d_qkv, 0, (rows + 272) * 3 * hid * 2);
+        // the padding is POISONED (0xFFFF = NaN in fp16 and bf16): rows past the last sequence are stale memory in the model path
+        // (ensure_ws never initialises the workspace tail), and no output may depend on them
+        cudaMemset(d_qkv, 0xff, (rows + 272) * 3 * hid * 2);
         cudaMemset(d_out, 0xff, rows * hid * 2);
         cudaMemcpy(d_qkv, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice);
         cudaStreamCreate(&st); cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -213,6 +213,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             if (g + 1 < G) issue_s(g + 1);
             const uint32_t sl = g & 1;
             const int i = g / ntile;
+            if (g == i * ntile && p.T < nmma) {
+                // V rows of the padded keys [T, nmma) belong to the NEXT sequence (or lie past the last one, where the buffer holds
+                // whatever was there before): their probabilities are exactly 0, but 0 * NaN/Inf would still poison every output row
+                // of this item.  Zero them once per K/V stage (a 128-B swizzled row stays inside its own 128 bytes), then make the
+                // generic-proxy stores visible to the UMMA operand reads.
+                const uint32_t v0 = smem_base + (i & 1) * (2 * KV_BYTES) + KV_BYTES + (uint32_t)p.T * 128;
+                for (int c = lane; c < (nmma - p.T) * 8; c += 32)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(v0 + 16 * c), "r"(0u) : "memory");
+                fence_proxy_async_smem();
+                __syncwarp();
+            }
             mbar_wait(p_full + 8 * sl, (g >> 1) & 1);
             tc_fence_after();
             if (elect_one()) {

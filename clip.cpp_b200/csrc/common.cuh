@@ -24,7 +24,7 @@ enum Epi : int {
     EPI_STORE16 = 0,      // out16 = (acc + bias) [* scale for the first scale_cols features]
     EPI_GELU16 = 1,       // out16 = gelu_tanh(acc + bias)          (clip.use_gelu = true)
     EPI_QGELU16 = 2,      // out16 = quick_gelu(acc + bias)         (clip.use_gelu = false)
-    EPI_RESID32 = 3,      // x32  += acc + bias                     (residual stream stays fp32)
+    /* 3 was a read-modify-write residual epilogue: latency-bound, replaced by the deferred add in LayerNorm */
     EPI_STORE32 = 4,      // out32 = acc + bias
 };
 
@@ -98,24 +98,6 @@ CB_DEVINL uint32_t mapa_rank0(uint32_t addr) {   // shared::cluster address of `
 }
 CB_DEVINL void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-CB_DEVINL bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-CB_DEVINL void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait_cluster(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > CB_WAIT_TIMEOUT_CYCLES) __trap();
-    }
 }
 CB_DEVINL void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -20,7 +20,7 @@
 //               pairs -> tcgen05.st.32x32b.x32 into A stage (i mod 4)                               -> a_full[j]
 //   warp 1      one elected thread issues tcgen05.mma (M128 N192 K16, kind::f16, A from TMEM, B from smem), fp32
 //               accumulators in TMEM; tcgen05.commit releases the X / A stages and signals the epilogue
-//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / scale / GELU / residual -> coalesced global stores;
+//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / scale / GELU -> coalesced global stores;
 //               double-buffered accumulators (2 x 192 TMEM columns) overlap it with the next tile's MMAs
 //   warp 2      TMEM alloc / dealloc   (TMEM map: acc0 [0,192) acc1 [192,384) A stages [384 + 32 j), j < 4)
 //
@@ -167,20 +167,7 @@ CB_DEVINL void unpack_block(uint32_t q, int t, uint32_t* __restrict__ out) {
 // element offsets are 32-bit (host checks M*ldo < 2^32) so each access costs one IADD + one IMAD.WIDE.
 template <int EPI, bool BF, bool FULL>
 CB_DEVINL void epilogue_chunk(const KParams& p, const uint32_t (&r)[32], uint32_t off, uint32_t ldo, int nvalid, float bias, float mul) {
-    if constexpr (EPI == EPI_RESID32) {
-        float* base = reinterpret_cast<float*>(p.out);
-        #pragma unroll
-        for (int h = 0; h < 2; h++) {              // two batches of 16 independent loads (register budget: 128/thread)
-            float old[16];
-            uint32_t o = off + (uint32_t)(16 * h) * ldo;
-            #pragma unroll
-            for (int j = 0; j < 16; j++, o += ldo) old[j] = (FULL || 16 * h + j < nvalid) ? base[o] : 0.f;
-            o = off + (uint32_t)(16 * h) * ldo;
-            #pragma unroll
-            for (int j = 0; j < 16; j++, o += ldo)
-                if (FULL || 16 * h + j < nvalid) base[o] = old[j] + (__uint_as_float(r[16 * h + j]) + bias);
-        }
-    } else if constexpr (EPI == EPI_STORE32) {
+    if constexpr (EPI == EPI_STORE32) {
         float* base = reinterpret_cast<float*>(p.out);
         uint32_t o = off;
         #pragma unroll
@@ -391,7 +378,6 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             case EPI_STORE16: epilogue_tile<EPI_STORE16, BF>(p, acc_addr, tok0, n, bias, mul); break;
             case EPI_GELU16: epilogue_tile<EPI_GELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
             case EPI_QGELU16: epilogue_tile<EPI_QGELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
-            case EPI_RESID32: epilogue_tile<EPI_RESID32, BF>(p, acc_addr, tok0, n, bias, mul); break;
             default: epilogue_tile<EPI_STORE32, BF>(p, acc_addr, tok0, n, bias, mul); break;
             }
             tc_fence_before();

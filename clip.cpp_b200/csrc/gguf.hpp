@@ -78,8 +78,13 @@ public:
         }
         tensors.resize(n_t);
         for (auto& t : tensors) {
-            if (!rd_str(off, t.name) || !rd(off, t.n_dims) || t.n_dims > 4) { err = "corrupt GGUF tensor info"; return false; }
-            for (uint32_t i = 0; i < t.n_dims; i++) if (!rd(off, t.ne[i])) { err = "corrupt GGUF tensor info"; return false; }
+            if (!rd_str(off, t.name) || !rd(off, t.n_dims) || t.n_dims < 1 || t.n_dims > 4) { err = "corrupt GGUF tensor info"; return false; }
+            uint64_t total = 1;
+            for (uint32_t i = 0; i < t.n_dims; i++) {
+                if (!rd(off, t.ne[i]) || t.ne[i] == 0 || t.ne[i] > (1ull << 40)) { err = "corrupt GGUF tensor info (dimension)"; return false; }
+                if (total > (1ull << 48) / t.ne[i]) { err = "corrupt GGUF tensor info (element count overflows)"; return false; }
+                total *= t.ne[i];
+            }
             if (!rd(off, t.type) || !rd(off, t.offset)) { err = "corrupt GGUF tensor info"; return false; }
         }
         alignment = 32;
@@ -92,7 +97,8 @@ public:
             const size_t bb = ggml_type_block_bytes(t.type), be = ggml_type_block_elems(t.type);
             if (!bb || t.ne[0] % be) { err = "tensor " + t.name + ": unsupported type or row length"; return false; }
             t.nbytes = (size_t)(t.nelements() / be) * bb;
-            if (data_start + t.offset + t.nbytes > size_) { err = "tensor " + t.name + " runs past end of file"; return false; }
+            // overflow-safe bounds: offset and length are checked against what is LEFT of the file, never summed first
+            if (data_start > size_ || t.offset > size_ - data_start || t.nbytes > size_ - data_start - t.offset) { err = "tensor " + t.name + " runs past end of file"; return false; }
             t.data = base_ + data_start + t.offset;
             tindex_[t.name] = i;
         }
@@ -108,12 +114,12 @@ public:
 
 private:
     template <class T> bool rd(size_t& off, T& v) const {
-        if (off + sizeof(T) > size_) return false;
+        if (off > size_ || sizeof(T) > size_ - off) return false;
         memcpy(&v, base_ + off, sizeof(T)); off += sizeof(T); return true;
     }
     bool rd_str(size_t& off, std::string& s) const {
         uint64_t n = 0;
-        if (!rd(off, n) || n > size_ || off + n > size_) return false;
+        if (!rd(off, n) || n > size_ - off) return false;
         s.assign((const char*)base_ + off, (size_t)n); off += (size_t)n; return true;
     }
     static size_t scalar_size(uint32_t t) {
@@ -122,7 +128,7 @@ private:
     }
     bool rd_scalar(size_t& off, uint32_t t, uint64_t& u, double& f) const {
         const size_t n = scalar_size(t);
-        if (!n || off + n > size_) return false;
+        if (!n || off > size_ || n > size_ - off) return false;
         const uint8_t* p = base_ + off; off += n;
         switch (t) {
         case GT_U8: case GT_BOOL: u = *p; f = (double)u; break;
@@ -149,7 +155,7 @@ private:
                 return true;
             }
             const size_t es = scalar_size(kv.arr_type);
-            if (!es || kv.arr_n > size_ || off + es * kv.arr_n > size_) return false;
+            if (!es || kv.arr_n > (size_ - off) / es) return false;
             off += es * (size_t)kv.arr_n;
             return true;
         }

@@ -1,6 +1,8 @@
 // host_ops.cpp -- CPU-side members of the clip.h interface.  These are the callers / data formats on either side of
-// the GPU hot path; they are written from the reference's documented behaviour,
-// not from its code, and each function cites the lines whose results it must reproduce.
+// the GPU hot path.  Tokenizer, GGUF reader / writer and file handling are own
+// designs; the bit-exact arithmetic kernels -- the bicubic tap table (keys_cubic / resize_taps, PIL's Resample.c as restated in
+// clip.cpp:728-794) and the block quantizers (quant_row, ggml.c:914-1116) -- necessarily follow the reference's operation order
+// step by step, because byte-identical output leaves no other choice.  Each function cites the lines whose results it reproduces.
 #include "host_ops.h"
 
 #include <float.h>
@@ -212,7 +214,7 @@ std::vector<int32_t> tokenize(const Vocab& v, const char* text) {
 // ---------------------------------------------------------------------------------------------------
 // preprocess: clip.cpp:728-927 -- PIL-style separable bicubic (Keys a = -0.5) with antialias support, clamp to
 // [0,255] after each pass, centre crop, (v/255 - mean)/std.  Arithmetic order is kept (double accumulation in
-// ascending tap order) so results are bit-identical to the reference (tests/test_host_ops.py).
+// ascending tap order) so results are bit-identical to the reference (tests/test_host_side.py).
 // ---------------------------------------------------------------------------------------------------
 namespace {
 inline double keys_cubic(double x) {
@@ -337,8 +339,8 @@ bool quantize_file(const char* inp, const char* outp, int itype, std::string& er
             o.data.resize((size_t)rows * rb);
             f32buf.resize((size_t)k);
             for (int64_t r = 0; r < rows; r++) {
-                dequant_row((int)t.type, t.data + (size_t)r * (t.type == 0 ? 4 : 2) * k, f32buf.data(), k);
-                quant_row(itype, f32buf.data(), o.data.data() + (size_t)r * rb, k);
+                if (!dequant_row((int)t.type, t.data + (size_t)r * (t.type == 0 ? 4 : 2) * k, f32buf.data(), k) ||
+                    !quant_row(itype, f32buf.data(), o.data.data() + (size_t)r * rb, k)) { err = "cannot convert tensor " + t.name; return false; }
             }
             o.type = (uint32_t)itype; o.ptr = o.data.data(); o.size = o.data.size();
         } else {

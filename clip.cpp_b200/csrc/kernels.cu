@@ -176,28 +176,12 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
     }
 }
 
-// logits[i, j] = <img_i, txt_j>; small (n_img x n_txt x d), one warp per output element group
-__global__ void __launch_bounds__(256) logits_kernel(const float* __restrict__ img, const float* __restrict__ txt,
-                                                     float* __restrict__ out, int n_img, int n_txt, int d) {
-    const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (w >= (size_t)n_img * n_txt) return;
-    const int i = (int)(w / n_txt), j = (int)(w % n_txt);
-    float s = 0.f;
-    for (int k = lane; k < d; k += 32) s += img[(size_t)i * d + k] * txt[(size_t)j * d + k];
-    s = warp_sum(s);
-    if (lane == 0) out[w] = s;
-}
-
-// p = (exp(s) + 1e-9) / sum  -- softmax_with_sorting's arithmetic without max subtraction (clip.cpp:1599-1607)
-__global__ void __launch_bounds__(256) softmax_plain_kernel(float* __restrict__ x, int rows, int cols) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (row >= rows) return;
-    float* r = x + (size_t)row * cols;
-    float s = 0.f;
-    for (int i = lane; i < cols; i += 32) { const float e = expf(r[i]) + 1e-9f; r[i] = e; s += e; }
-    s = warp_sum(s);
-    for (int i = lane; i < cols; i += 32) r[i] = r[i] / s;
+__global__ void fill_last_kernel(const int32_t* __restrict__ lens, int32_t* __restrict__ last, int n, int seq_len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = lens ? lens[i] : seq_len;
+    v = v < 1 ? 1 : (v > seq_len ? seq_len : v);
+    last[i] = v - 1;
 }
 
 // ---- debug scalar GEMM from raw ggml rows -----------------------------------------------------------
@@ -238,8 +222,7 @@ __global__ void naive_gemm_kernel(const uint16_t* __restrict__ x, int x_bf16, co
     }
     float v = acc + (bias ? bias[n] : 0.f);
     const size_t o = (size_t)m * ldo + n;
-    if (epi == EPI_RESID32) reinterpret_cast<float*>(out)[o] += v;
-    else if (epi == EPI_STORE32) reinterpret_cast<float*>(out)[o] = v;
+    if (epi == EPI_STORE32) reinterpret_cast<float*>(out)[o] = v;
     else {
         if (epi == EPI_GELU16) v = gelu_tanh(v);
         else if (epi == EPI_QGELU16) v = gelu_quick(v);
@@ -298,15 +281,9 @@ void launch_gather_rows(const float* src, float* dst, int rows, int h, int strid
     else gather_rows_kernel<false><<<rows_grid(rows, 8), 256, 0, st>>>(src, dst, rows, h, stride_rows, offs, (const uint16_t*)delta16);
 }
 
-void launch_logits(const float* img, const float* txt, float* logits, int n_img, int n_txt, int d, cudaStream_t st) {
-    const size_t n = (size_t)n_img * n_txt;
-    if (!n) return;
-    logits_kernel<<<(int)((n + 7) / 8), 256, 0, st>>>(img, txt, logits, n_img, n_txt, d);
-}
-
-void launch_softmax_plain(float* logits, int rows, int cols, cudaStream_t st) {
-    if (rows <= 0) return;
-    softmax_plain_kernel<<<rows_grid(rows, 8), 256, 0, st>>>(logits, rows, cols);
+void launch_fill_last(const int32_t* lens, int32_t* last, int n, int seq_len, cudaStream_t st) {
+    if (n <= 0) return;
+    fill_last_kernel<<<(n + 255) / 256, 256, 0, st>>>(lens, last, n, seq_len);
 }
 
 void launch_naive_gemm(const void* x16, int x_bf16, const void* w_ggml, int qtype, const float* bias, void* out, int M, int N,

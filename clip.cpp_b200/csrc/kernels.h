@@ -45,9 +45,19 @@ void launch_l2norm(const float* v, float* out, int rows, int d, int normalize, c
 void launch_gather_rows(const float* src, float* dst, int rows, int h, int stride_rows, const int32_t* offs, const void* delta16,
                         int bf16, cudaStream_t st);   // dst = src[idx] (+ delta16[idx])
 
-// zero-shot scoring (clip.cpp:1591-1622 semantics per row): p = (exp(s) + 1e-9) / sum
-void launch_logits(const float* img, const float* txt, float* logits, int n_img, int n_txt, int d, cudaStream_t st);
-void launch_softmax_plain(float* logits, int rows, int cols, cudaStream_t st);
+// text: last[i] = clamp(lens ? lens[i] : seq_len, 1, seq_len) - 1  (index of the EOT row, clip.cpp:1154-1155), on the device
+void launch_fill_last(const int32_t* lens, int32_t* last, int n, int seq_len, cudaStream_t st);
+
+// ---- scoring (search.cu) ----------------------------------------------------------------------------------------------
+// S[i, j] = <a_i, b_j> fp32, one sequential fmaf chain per element (clip_similarity_score, clip.cpp:1525-1532); row stride lds
+void launch_similarity(const float* a, const float* b, float* s, int na, int nb, int d, size_t lds, cudaStream_t st);
+// in place p = (exp(s) + 1e-9) / sum with softmax_with_sorting's rounding points (clip.cpp:1599-1607)
+void launch_softmax_ref(float* logits, int rows, int cols, size_t ld, cudaStream_t st);
+// one top-k stage: every slice of topk_slice() candidates of a row is sorted (value desc, index asc) and its best kk are written to
+// out[row, out_off + slice * kk ...]; in_idx == nullptr: candidate j has index idx_base + j
+int topk_slice();
+void launch_topk_stage(const float* vals, const int* in_idx, size_t ld, int rows, int n, int idx_base, int kk, float* out_v, int* out_i,
+                       size_t out_ld, int out_off, cudaStream_t st);
 
 }  // namespace cb
 struct clip_ctx;

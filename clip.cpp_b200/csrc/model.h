@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/clip_b200.h"
+#include "dist.h"
 #include "gemm.h"
 #include "host_ops.h"
 
@@ -100,4 +101,18 @@ struct clip_ctx {
     std::vector<cudaEvent_t> ev_pool;
     cb::PreArena pre[2];
     std::mutex mu;
+    cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};   // clip_b200_mark stopwatch slots (per context = per device)
+    // pinned staging for PAGEABLE caller buffers (clip_image_preprocess hands out new float[]): filled by host threads, one async
+    // H2D per micro-batch -- pageable cudaMemcpyAsync would be staged synchronously by the driver, image by image
+    float* h_stage[2] = {nullptr, nullptr};
+    size_t h_stage_cap = 0;                 // floats per buffer
+    // scoring scratch (search.cu), grow-only
+    float* d_logits = nullptr; size_t d_logits_cap = 0;
+    float* d_cand_v[2] = {nullptr, nullptr}; int* d_cand_i[2] = {nullptr, nullptr}; size_t d_cand_cap = 0;
+    float* d_emb[2] = {nullptr, nullptr}; size_t d_emb_cap[2] = {0, 0};     // image / text embeddings kept on the device (zero-shot)
+    double* d_scalars = nullptr;            // 16 doubles for the tiny all-reduces (barrier, max over ranks)
+    // ---- multi-GPU (dist.h) ------------------------------------------------------------------------------------------
+    cb::DistComm dist;                      // this replica's NCCL communicator (ranks mode or devices mode); world == 1: none
+    std::vector<clip_ctx*> replicas;        // devices mode, on the leader only: every replica, this context first
+    bool is_replica = false;                // owned by a leader: never handed to the caller
 };

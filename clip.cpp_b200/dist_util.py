@@ -5,24 +5,21 @@ from __future__ import annotations
 
 
 def shard_bounds(n: int, rank: int, world: int):
-    """Contiguous shards of n // world items; the last rank takes the remainder."""
-    per = n // world
-    lo = rank * per
-    hi = n if rank == world - 1 else lo + per
-    return lo, hi
+    """Contiguous balanced shards [n*r//w, n*(r+1)//w) -- the rule the library uses in devices mode (csrc/dist.h)."""
+    return n * rank // world, n * (rank + 1) // world
 
 
 def all_gather_rows(dist, local, n_total: int, world: int):
     """local: [n_local, d] tensor on this rank -> [n_total, d] on every rank (ragged shards are padded to the largest)."""
     import torch
-    per, last = n_total // world, n_total - (world - 1) * (n_total // world)
-    width = max(per, last)
+    sizes = [shard_bounds(n_total, r, world)[1] - shard_bounds(n_total, r, world)[0] for r in range(world)]
+    width = max(sizes)
     d = local.shape[1]
     pad = torch.zeros((width, d), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = torch.empty((world * width, d), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, pad)
-    rows = [out[r * width: r * width + (last if r == world - 1 else per)] for r in range(world)]
+    rows = [out[r * width: r * width + sizes[r]] for r in range(world)]
     return torch.cat(rows, 0)
 
 

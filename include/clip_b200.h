@@ -147,7 +147,7 @@ bool clip_zero_shot_label_image(struct clip_ctx * ctx, const int n_threads, cons
                                 const char ** labels, const size_t n_labels, float * scores, int * indices);
 
 /* clip.h:109, clip.cpp:1661-1844 -- f32/f16 GGUF -> q4_0(2) q4_1(3) q5_0(6) q5_1(7) q8_0(8); output is byte-identical
- * to the reference's (tests/test_quantize.py) */
+ * to the reference's (tests/test_host_side.py) */
 bool clip_model_quantize(const char * fname_inp, const char * fname_out, const int itype);
 
 /* =====================================================================================================
@@ -168,10 +168,54 @@ bool clip_b200_image_encode_device(const struct clip_ctx * ctx, const void * d_p
 bool clip_b200_text_encode_device(const struct clip_ctx * ctx, const void * d_ids, const void * d_lens, size_t n,
                                   int seq_len, void * d_vec, bool normalize);
 
-/* Batched zero-shot scoring on the device (clip.cpp:1624-1659 semantics per image, un-normalised embeddings):
- * d_img_vec [n_img, d], d_txt_vec [n_txt, d] -> host scores/indices [n_img, top_k] sorted descending. */
+/* Batched zero-shot scoring on the device (clip.cpp:1624-1659 semantics per image): d_img_vec [n_img, d], d_txt_vec [n_txt, d]
+ * -> host scores/indices [n_img, top_k], best first; similarity matrix, softmax and top-k selection all run on the GPU. */
 bool clip_b200_zero_shot_batch(const struct clip_ctx * ctx, const void * d_img_vec, size_t n_img, const void * d_txt_vec,
                                size_t n_txt, float * scores, int * indices, int top_k);
+
+/* Nearest-neighbour search on the device (stands in for USearch in examples/image-search/search.cpp:114-158): raw dot products
+ * (cosine similarity for normalised embeddings) of n_queries x n_db device-resident vectors, best top_k per query to the host. */
+bool clip_b200_topk_search(const struct clip_ctx * ctx, const void * d_queries, size_t n_queries, const void * d_db, size_t n_db,
+                           int top_k, float * scores, int * indices);
+
+/* Batched zero-shot labelling, the batch form of clip_zero_shot_label_image (clip.h:106-107, clip.cpp:1624-1659): n images x
+ * n_labels token sequences -> scores / indices [n, top_k], best first (p = (exp(s)+1e-9)/sum over ALL labels, clip.cpp:1591-1622).
+ * normalize = false reproduces the reference (un-normalised embeddings).  Works in every multi-GPU mode (see below): in devices
+ * mode images and labels are sharded over the GPUs and the label embeddings all-gathered; in ranks mode the caller passes this
+ * rank's images and this rank's label shard (same count on every rank; global label index = rank * n_labels + j). */
+bool clip_b200_zero_shot_images(const struct clip_ctx * ctx, const int n_threads, const struct clip_image_f32_batch * imgs,
+                                const struct clip_tokens * labels, const size_t n_labels, const bool normalize, int top_k,
+                                float * scores, int * indices);
+
+/* ---- multi-GPU inside the library (csrc/dist.h; the reference's analogue is ggml-cuda.cu:404-407, 5934-5957) -----------------
+ * devices mode: set CLIP_B200_DEVICES=0,1,...|all before clip_model_load: ONE context drives a replica per GPU (NCCL communicators
+ *   from ncclCommInitAll); clip_image_batch_encode / clip_text_batch_encode / clip_b200_zero_shot_images shard their batch
+ *   contiguously and each GPU copies its slice of the result into the caller's buffer.
+ * ranks mode:   one process per GPU (torchrun, mpirun, ...): clip_b200_dist_init joins an NCCL communicator (ncclCommInitRank);
+ *   rendezvous = NULL takes the 128-byte unique id from a file named after MASTER_PORT and the launcher's pid (single node), or
+ *   exchange clip_b200_dist_unique_id's output yourself and call clip_b200_dist_init_with_id.  CLIP_B200_DIST=env makes
+ *   clip_model_load do this from RANK / WORLD_SIZE / LOCAL_RANK.  The *_all entry points encode this rank's items and return the
+ *   embeddings of ALL ranks, rank-major (one in-place ncclAllGather on the launch stream; every rank must pass the same count).
+ * libnccl.so.2 is dlopen'ed on first use; no torch, no MPI. */
+bool clip_b200_dist_unique_id(void * out128);
+bool clip_b200_dist_init_with_id(struct clip_ctx * ctx, int rank, int world, const void * id128);
+bool clip_b200_dist_init(struct clip_ctx * ctx, int rank, int world, const char * rendezvous);
+int  clip_b200_dist_rank(const struct clip_ctx * ctx);
+int  clip_b200_dist_world(const struct clip_ctx * ctx);
+int  clip_b200_device_count(const struct clip_ctx * ctx);           /* GPUs behind this context (devices mode), else 1 */
+int  clip_b200_nccl_version(void);                                  /* 0 when libnccl cannot be loaded */
+int  clip_b200_cuda_device_count(void);                             /* visible CUDA devices (0 without a driver) */
+bool clip_b200_dist_barrier(const struct clip_ctx * ctx);           /* all ranks + device synchronize */
+bool clip_b200_dist_max_f64(const struct clip_ctx * ctx, double * vals, int n);   /* element-wise max over ranks, n <= 16 */
+bool clip_b200_dist_all_gather(const struct clip_ctx * ctx, const void * d_send, void * d_recv, size_t bytes_per_rank);
+bool clip_b200_image_encode_device_all(const struct clip_ctx * ctx, const void * d_pixels, size_t n_local, void * d_vec_all,
+                                       bool normalize);
+bool clip_b200_text_encode_device_all(const struct clip_ctx * ctx, const void * d_ids, const void * d_lens, size_t n_local,
+                                      int seq_len, void * d_vec_all, bool normalize);
+bool clip_b200_image_batch_encode_all(const struct clip_ctx * ctx, const int n_threads, const struct clip_image_f32_batch * imgs,
+                                      float * vec_all, const bool normalize);
+bool clip_b200_text_batch_encode_all(const struct clip_ctx * ctx, const int n_threads, const struct clip_tokens * seqs,
+                                     const size_t n, float * vec_all, const bool normalize);
 
 /* memory + stream helpers so that a plain C caller needs no CUDA headers */
 void * clip_b200_device_malloc(const struct clip_ctx * ctx, size_t bytes);

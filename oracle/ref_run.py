@@ -17,14 +17,18 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
+REF_LIB = os.path.join(HERE, "_ref", "libclip_ref.so")      # the unmodified reference (oracle/Makefile)
 
 
 def available() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libclip_ref.so"))
 
 
-def run_reference(model: str, images=None, token_seqs=None, n_threads: int = 0, normalize: bool = True, timing: bool = False):
-    """images: [n,S,S,3] f32 or None; token_seqs: list of int32 arrays or None.  Returns dict(img=, txt=[, img_s=, txt_s=])."""
+def run_reference(model: str, images=None, token_seqs=None, n_threads: int = 0, normalize: bool = True, timing: bool = False,
+                  u8_image=None, texts=None):
+    """images: [n,S,S,3] f32 or None; token_seqs: list of int32 arrays or None.  Returns dict(img=, txt=[, img_s=, txt_s=]).
+    u8_image [ny,nx,3] + texts (list of str): additionally runs clip_compare_text_and_image per text (res["cmp"]) and
+    clip_zero_shot_label_image over all texts (res["zsl_scores"], res["zsl_idx"]) -- clip.cpp:1534-1571, 1624-1659."""
     with tempfile.TemporaryDirectory() as td:
         inp, out = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
         d = {"normalize": np.array(int(normalize)), "n_threads": np.array(n_threads)}
@@ -33,6 +37,9 @@ def run_reference(model: str, images=None, token_seqs=None, n_threads: int = 0, 
         if token_seqs is not None:
             d["tok_flat"] = np.concatenate([np.asarray(t, np.int32) for t in token_seqs]) if len(token_seqs) else np.zeros(0, np.int32)
             d["tok_lens"] = np.array([len(t) for t in token_seqs], np.int64)
+        if u8_image is not None and texts:
+            d["u8"] = np.ascontiguousarray(u8_image, np.uint8)
+            d["texts"] = np.array(list(texts))
         np.savez(inp, **d)
         r = subprocess.run([sys.executable, os.path.abspath(__file__), model, inp, out], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         if r.returncode != 0:
@@ -49,7 +56,7 @@ def _main():
     z = np.load(inp)
     nt = int(z["n_threads"]) or (os.cpu_count() or 4)
     normalize = bool(int(z["normalize"]))
-    ref = bd.ClipLib(bd.REF_LIB)
+    ref = bd.ClipLib(REF_LIB)
     ctx = ref.load(model, 0)
     res = {}
     if "images" in z.files:
@@ -65,6 +72,12 @@ def _main():
         res["txt"] = np.stack([ref.text_encode(ctx, flat[offs[i]:offs[i + 1]], normalize, nt) for i in range(len(lens))]) \
             if len(lens) else np.zeros((0, 1), np.float32)
         res["txt_s"] = np.array(time.perf_counter() - t0)
+    if "u8" in z.files:
+        # scoring entry points LAST and zero-shot before compare: they run text + image graphs back to back in one context
+        u8, texts = z["u8"], [str(t) for t in z["texts"]]
+        sc, ix = ref.zero_shot_label_image(ctx, u8, texts, nt)
+        res["zsl_scores"], res["zsl_idx"] = sc, ix
+        res["cmp"] = np.array([ref.compare_text_and_image(ctx, t, u8, nt) for t in texts], np.float32)
     res["threads"] = np.array(nt)
     np.savez(out, **res)
 

@@ -26,7 +26,7 @@ def golden(geom):
 
 def model_file(geom: str, ftype: str, prod: "bd.ClipLib") -> str:
     """(geom, SEED, ftype) -> path; f16/f32 written from the seed, q* made with the PRODUCT's clip_model_quantize
-    (byte-identical to the reference's: tests/test_quantize.py)."""
+    (byte-identical to the reference's: tests/test_host_side.py)."""
     path = sg.model_path(geom, SEED, ftype)
     if not os.path.exists(path):
         if ftype in ("f32", "f16"):

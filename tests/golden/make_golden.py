@@ -69,7 +69,7 @@ def main():
         plan.update(PLAN_FULL)
     if a.only:
         plan = {k: v for k, v in {**PLAN, **PLAN_FULL}.items() if k in a.only.split(",")}
-    ref = bd.ClipLib(bd.REF_LIB)
+    ref = bd.ClipLib(ref_run.REF_LIB)
     # the reference prints one line per tensor while quantizing: silence fd 1 around it
     def quiet_quant(src, dst, it):
         sys.stdout.flush()

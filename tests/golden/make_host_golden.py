@@ -9,7 +9,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "clip.cpp_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import binding as bd          # noqa: E402
+import ref_run                # noqa: E402
 import synth_gguf as sg       # noqa: E402
 
 TEXTS = ["a photo of a cat", "a photo of the dog's red apple", "two  cats,   3 dogs!", "it's 12 o'clock... we've won",
@@ -30,7 +32,7 @@ def main():
     model = sg.model_path("tiny", 1234, "f16")
     if not os.path.exists(model):
         sg.write_model(model, sg.GEOMETRIES["tiny"], 1234, 1)
-    ref = bd.ClipLib(bd.REF_LIB)
+    ref = bd.ClipLib(ref_run.REF_LIB)
     ctx = ref.load(model, 0)
     out = {"model_sha": sg.sha256_file(model), "tokens": {}, "preprocess": []}
     for t in TEXTS:

@@ -92,9 +92,9 @@ def test_tokenizer_and_preprocess_match_live_reference(prod):
     model = model_file("tiny", "f16", prod)
     texts = ["the red apple isn't a dog", "  double  spaces and 42 numbers!!", "mixed'case I'LL"]
     u8 = _synth_u8(123, 77, 99)
-    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import binding as bd; r = bd.ClipLib(bd.REF_LIB); c = r.load(%r, 0);"
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r); import binding as bd, ref_run; r = bd.ClipLib(ref_run.REF_LIB); c = r.load(%r, 0);"
             "print(json.dumps({'tok': [[int(v) for v in r.tokenize(c, t)] for t in %r], 'pre': r.preprocess(c, np.load(sys.argv[1])).ravel().tolist()}))"
-            % (os.path.join(os.path.dirname(GOLDEN), "..", "clip.cpp_b200"), model, texts))
+            % (os.path.join(os.path.dirname(GOLDEN), "..", "clip.cpp_b200"), os.path.join(os.path.dirname(GOLDEN), "..", "oracle"), model, texts))
     with tempfile.NamedTemporaryFile(suffix=".npy") as f:
         np.save(f.name, u8)
         res = json.loads(subprocess.run([sys.executable, "-c", code, f.name], capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
