@@ -75,6 +75,7 @@ EXTENSION_SYMBOLS = [
     "clip_b200_dist_init", "clip_b200_dist_rank", "clip_b200_dist_world", "clip_b200_device_count", "clip_b200_nccl_version", "clip_b200_cuda_device_count",
     "clip_b200_dist_barrier", "clip_b200_dist_max_f64", "clip_b200_dist_all_gather", "clip_b200_image_encode_device_all",
     "clip_b200_text_encode_device_all", "clip_b200_image_batch_encode_all", "clip_b200_text_batch_encode_all",
+    "clip_b200_debug_rendezvous", "clip_b200_debug_shard_bounds",
 ]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -198,6 +199,10 @@ class ClipLib:
             L.clip_b200_nccl_version.argtypes = []
             L.clip_b200_cuda_device_count.restype = C.c_int
             L.clip_b200_cuda_device_count.argtypes = []
+            L.clip_b200_debug_rendezvous.restype = C.c_int
+            L.clip_b200_debug_rendezvous.argtypes = [ip, ip, C.c_char_p, vp]
+            L.clip_b200_debug_shard_bounds.restype = None
+            L.clip_b200_debug_shard_bounds.argtypes = [C.c_size_t, ip, ip, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
             L.clip_b200_dist_barrier.restype = C.c_bool
             L.clip_b200_dist_barrier.argtypes = [vp]
             L.clip_b200_dist_max_f64.restype = C.c_bool

@@ -1520,6 +1520,13 @@ int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int caus
 
 
 // ---- CPU-only test hooks (no context / GPU needed) ----------------------------------------------------------
+// ranks-mode rendezvous of the NCCL unique id (dist.cpp) without a GPU: rank 0 publishes, the others read the same 128 bytes
+int clip_b200_debug_rendezvous(int rank, int world, const char* path, void* out128) {
+    std::string e;
+    if (!dist_rendezvous_id(rank, world, path, out128, e)) { set_err(e); return 1; }
+    return 0;
+}
+void clip_b200_debug_shard_bounds(size_t n, int r, int w, size_t* lo, size_t* hi) { shard_bounds(n, r, w, *lo, *hi); }
 int clip_b200_debug_repack_roundtrip(int qtype, const void* rows, int N, int K) {
     const size_t raw = (size_t)N * (K / 32) * wpack_ggml_block_bytes(qtype);
     std::vector<uint8_t> packed(wpack_total_bytes(qtype, N, K)), back(raw);

@@ -81,6 +81,9 @@ GEOMETRIES = {
     # odd patch size (K = 3*14*14 = 588, not a multiple of 64) and 257 positions at small width
     "small-p14": Geometry("small-p14", image_size=224, patch_size=14, v_hidden=256, v_ff=512, v_heads=4,
                           v_layers=12, t_hidden=128, t_ff=256, t_heads=2, t_layers=12, proj_dim=128),
+    # ViT-L/14@336 token count (24*24 + 1 = 577 > 257: the long-sequence attention path) at small width
+    "small-p14-336": Geometry("small-p14-336", image_size=336, patch_size=14, v_hidden=128, v_ff=256, v_heads=2,
+                              v_layers=12, t_hidden=128, t_ff=256, t_heads=2, t_layers=12, proj_dim=128),
 }
 
 

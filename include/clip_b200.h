@@ -265,6 +265,8 @@ int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int caus
 
 /* CPU-only TEST HOOKS (no context, no GPU): lossless re-tiling check, tokenizer and preprocess without a model context */
 int clip_b200_debug_repack_roundtrip(int qtype, const void * rows, int N, int K);
+int clip_b200_debug_rendezvous(int rank, int world, const char * path, void * out128);     /* ranks-mode id exchange (csrc/dist.cpp) */
+void clip_b200_debug_shard_bounds(size_t n, int r, int w, size_t * lo, size_t * hi);        /* devices-mode sharding rule */
 int clip_b200_debug_tokenize(const char * gguf_path, const char * text, int32_t * out, int cap);
 int clip_b200_debug_preprocess(const uint8_t * rgb, int nx, int ny, int out_size, const float * mean, const float * stdv,
                                float * out);

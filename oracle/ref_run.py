@@ -20,18 +20,41 @@ ROOT = os.path.dirname(HERE)
 REF_LIB = os.path.join(HERE, "_ref", "libclip_ref.so")      # the unmodified reference (oracle/Makefile)
 
 
+REF_LIB_V4 = os.path.join(HERE, "_ref", "libclip_ref_v4.so")   # same sources, -march=x86-64-v4 (AVX-512 hosts, timing only)
+
+
 def available() -> bool:
     return os.path.exists(os.path.join(HERE, "_ref", "libclip_ref.so"))
 
 
+def host_has_avx512() -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    fl = set(line.split(":", 1)[1].split())
+                    return {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= fl
+    except OSError:
+        pass
+    return False
+
+
+def timing_lib():
+    """(path, isa description) of the build the CPU-baseline legs should time: the AVX-512 build on AVX-512 hosts (what the
+    reference's own CLIP_NATIVE=ON build selects there), else the AVX2 one.  Parity work always uses REF_LIB."""
+    if os.environ.get("CLIP_REF_ISA", "") != "avx2" and os.path.exists(REF_LIB_V4) and host_has_avx512():
+        return REF_LIB_V4, "reference built -O3 -march=x86-64-v4 (AVX-512 host)"
+    return REF_LIB, "reference built -O3 -mavx2 -mfma -mf16c (ggml's AVX2 kernels)"
+
+
 def run_reference(model: str, images=None, token_seqs=None, n_threads: int = 0, normalize: bool = True, timing: bool = False,
-                  u8_image=None, texts=None):
+                  u8_image=None, texts=None, lib_path: str = None):
     """images: [n,S,S,3] f32 or None; token_seqs: list of int32 arrays or None.  Returns dict(img=, txt=[, img_s=, txt_s=]).
     u8_image [ny,nx,3] + texts (list of str): additionally runs clip_compare_text_and_image per text (res["cmp"]) and
     clip_zero_shot_label_image over all texts (res["zsl_scores"], res["zsl_idx"]) -- clip.cpp:1534-1571, 1624-1659."""
     with tempfile.TemporaryDirectory() as td:
         inp, out = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
-        d = {"normalize": np.array(int(normalize)), "n_threads": np.array(n_threads)}
+        d = {"normalize": np.array(int(normalize)), "n_threads": np.array(n_threads), "lib": np.array(lib_path or REF_LIB)}
         if images is not None:
             d["images"] = np.ascontiguousarray(images, np.float32)
         if token_seqs is not None:
@@ -56,7 +79,7 @@ def _main():
     z = np.load(inp)
     nt = int(z["n_threads"]) or (os.cpu_count() or 4)
     normalize = bool(int(z["normalize"]))
-    ref = bd.ClipLib(REF_LIB)
+    ref = bd.ClipLib(str(z["lib"]) if "lib" in z.files else REF_LIB)
     ctx = ref.load(model, 0)
     res = {}
     if "images" in z.files:

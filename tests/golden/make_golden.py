@@ -31,10 +31,11 @@ PLAN = {
     "tiny": dict(ftypes=list(FTYPES), n_img=4, n_txt=8),
     "tiny-gelu": dict(ftypes=["f16", "q4_0"], n_img=2, n_txt=2),
     "small-p14": dict(ftypes=["f16", "q4_0", "q8_0"], n_img=2, n_txt=2),
+    "small-p14-336": dict(ftypes=["f16", "q4_0"], n_img=2, n_txt=2),
 }
 PLAN_FULL = {
-    "vit-b32": dict(ftypes=["f16", "q4_0", "q8_0"], n_img=3, n_txt=3),
-    "vit-l14": dict(ftypes=["f16", "q4_0", "q8_0"], n_img=2, n_txt=2),
+    "vit-b32": dict(ftypes=["f16", "q4_0", "q4_1", "q5_0", "q5_1", "q8_0"], n_img=3, n_txt=3),
+    "vit-l14": dict(ftypes=["f16", "q4_0", "q4_1", "q5_0", "q5_1", "q8_0"], n_img=3, n_txt=3),
 }
 
 

@@ -51,14 +51,20 @@ def test_patch14_257_positions(prod, ft):
     _check(prod, "small-p14", ft)
 
 
+@pytest.mark.parametrize("ft", ["f16", "q4_0"])
+def test_patch14_336_577_positions(prod, ft):
+    """ViT-L/14@336 token count (577 > 257: long-sequence attention path) end to end against the reference"""
+    _check(prod, "small-p14-336", ft)
+
+
 @pytest.mark.slow
-@pytest.mark.parametrize("ft", ["f16", "q4_0", "q8_0"])
+@pytest.mark.parametrize("ft", ["f16", "q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
 def test_vit_b32_true_geometry(prod, ft):
     _check(prod, "vit-b32", ft)
 
 
 @pytest.mark.slow
-@pytest.mark.parametrize("ft", ["f16", "q4_0", "q8_0"])
+@pytest.mark.parametrize("ft", ["f16", "q4_0", "q4_1", "q5_0", "q5_1", "q8_0"])
 def test_vit_l14_true_geometry(prod, ft):
     _check(prod, "vit-l14", ft)
 

@@ -66,3 +66,25 @@ def test_bad_inputs(prod, ctx):
     assert prod.image_batch_encode_u8(ctx, []).shape[0] == 0
     with pytest.raises(RuntimeError):
         prod.image_batch_encode_u8(ctx, [np.zeros((0, 5, 3), np.uint8)])
+
+
+def test_device_preprocess_matches_reference_golden_directly(prod, ctx):
+    """the DEVICE output against the sha256 of what the reference's clip_image_preprocess produced (tests/golden/host_ops.json,
+    written by make_host_golden.py from oracle/_ref) -- no detour through the library's own host path"""
+    import hashlib
+    import json
+    import os
+    from _util import GOLDEN
+    host = json.load(open(os.path.join(GOLDEN, "host_ops.json")))
+
+    def synth_u8(nx, ny, seed):        # same generator as tests/golden/make_host_golden.py
+        rng = np.random.Generator(np.random.PCG64(seed))
+        base = rng.integers(0, 256, size=(ny // 8 + 2, nx // 8 + 2, 3)).astype(np.float32)
+        img = np.kron(base, np.ones((8, 8, 1), np.float32))[:ny, :nx]
+        img += rng.normal(0, 12, size=img.shape).astype(np.float32)
+        return np.clip(img, 0, 255).astype(np.uint8)
+
+    imgs = [synth_u8(e["nx"], e["ny"], e["seed"]) for e in host["preprocess"]]
+    dev = prod.preprocess_device(ctx, imgs)
+    for e, out in zip(host["preprocess"], dev):
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == e["sha256"], e
