@@ -79,7 +79,7 @@ EXTENSION_SYMBOLS = [
 ]
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(HERE, "libclip_b200.so")
+PRODUCT_LIB = os.environ.get("CLIP_B200_LIB") or os.path.join(HERE, "libclip_b200.so")     # CLIP_B200_LIB: experiment builds only
 
 
 class ClipLib:

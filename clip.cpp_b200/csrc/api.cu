@@ -241,7 +241,10 @@ bool ensure_ws(clip_ctx* c, Tower& tw, int items, int T, bool vision) {
               make_tma_2d_16bit(&w.map_sel, w.sel16, items, h, h, GEMM_BN) &&
               make_tma_2d_16bit(&w.map_a_half, w.a, rows, h, h, GEMM_BN / 2) && make_tma_2d_16bit(&w.map_g_half, w.g, rows, tw.ff, tw.ff, GEMM_BN / 2) &&
               make_tma_2d_16bit(&w.map_q128, w.qkv, rows, 3 * h, 3 * h, 128) && make_tma_2d_16bit(&w.map_kv256, w.qkv, rows, 3 * h, 3 * h, 256) &&
-              make_tma_2d_16bit(&w.map_kv16, w.qkv, rows, 3 * h, 3 * h, 16);
+              make_tma_2d_16bit(&w.map_kv16, w.qkv, rows, 3 * h, 3 * h, 16) &&
+              make_tma_2d_16bit_plain(&w.map_out_qkv, w.qkv, rows, 3 * h, 3 * h, GEMM_OUT_BOX, GEMM_OUT_BOX) &&
+              make_tma_2d_16bit_plain(&w.map_out_d, w.d, rows, h, h, GEMM_OUT_BOX, GEMM_OUT_BOX) &&
+              make_tma_2d_16bit_plain(&w.map_out_g, w.g, rows, tw.ff, tw.ff, GEMM_OUT_BOX, GEMM_OUT_BOX);
     if (vision) {
         const size_t per = (size_t)tw.image_size * tw.image_size * 3;
         if (!dev_alloc(c, &w.pixels[0], items * per) || !dev_alloc(c, &w.pixels[1], items * per) ||
@@ -255,7 +258,7 @@ bool ensure_ws(clip_ctx* c, Tower& tw, int items, int T, bool vision) {
 }
 
 bool run_linear(clip_ctx* c, const Linear& L, const TmaMap* xmap, const void* xptr, bool x_bf16, int M, void* out, int ldo, int epi,
-                int out_bf16, int scale_cols = 0, float scale = 1.f, const TmaMap* xmap_half = nullptr) {
+                int out_bf16, int scale_cols = 0, float scale = 1.f, const TmaMap* xmap_half = nullptr, const TmaMap* out_map = nullptr) {
     Scope s(c, K_GEMM);
     if (c->debug_naive) {
         launch_naive_gemm(xptr, x_bf16, L.d_raw, L.qtype, L.d_bias, out, M, L.N, L.K, ldo, epi, out_bf16, scale_cols, scale, c->stream);
@@ -265,7 +268,7 @@ bool run_linear(clip_ctx* c, const Linear& L, const TmaMap* xmap, const void* xp
     GemmArgs a;
     a.x_map = xmap; a.x_half_map = xmap_half; a.w_map = &L.w_map; a.w_packed = L.d_w; a.qtype = L.qtype; a.operand_bf16 = x_bf16;
     a.bias = L.d_bias; a.out = out; a.M = M; a.N = L.N; a.K = L.K; a.ldo = ldo; a.epi = epi; a.out_bf16 = out_bf16;
-    a.scale_cols = scale_cols; a.scale = scale;
+    a.scale_cols = scale_cols; a.scale = scale; a.out_map = out_map;
     CK(gemm_launch(a, c->stream, c->num_sms, nullptr));
     return true;
 }
@@ -281,7 +284,7 @@ bool run_blocks(clip_ctx* c, Tower& tw, int nseq, int T, bool causal) {
     bool pending = false;
     for (auto& l : tw.L) {
         { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln1_g, l.ln1_b, pending ? w.d : nullptr, w.a, bf, c->stream); }
-        if (!run_linear(c, l.qkv, &w.map_a, w.a, bf, M, w.qkv, 3 * h, EPI_STORE16, bf, h, qscale, &w.map_a_half)) return false;
+        if (!run_linear(c, l.qkv, &w.map_a, w.a, bf, M, w.qkv, 3 * h, EPI_STORE16, bf, h, qscale, &w.map_a_half, &w.map_out_qkv)) return false;
         if (c->attn_tc && attention_tc_supported(T)) {
             const int q_done = attention_tc_tiles(T) * 128;
             { Scope s(c, K_ATTN); CK(launch_attention_tc(&w.map_q128, &w.map_kv256, &w.map_kv16, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, c->num_sms, c->stream)); }
@@ -289,10 +292,10 @@ bool run_blocks(clip_ctx* c, Tower& tw, int nseq, int T, bool causal) {
         } else {
             Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, 0, c->stream);
         }
-        if (!run_linear(c, l.out, &w.map_a, w.a, bf, M, w.d, h, EPI_STORE16, bf, 0, 1.f, &w.map_a_half)) return false;
+        if (!run_linear(c, l.out, &w.map_a, w.a, bf, M, w.d, h, EPI_STORE16, bf, 0, 1.f, &w.map_a_half, &w.map_out_d)) return false;
         { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln2_g, l.ln2_b, w.d, w.a, bf, c->stream); }
-        if (!run_linear(c, l.fc1, &w.map_a, w.a, bf, M, w.g, tw.ff, c->use_gelu ? EPI_GELU16 : EPI_QGELU16, bf, 0, 1.f, &w.map_a_half)) return false;
-        if (!run_linear(c, l.fc2, &w.map_g, w.g, bf, M, w.d, h, EPI_STORE16, bf, 0, 1.f, &w.map_g_half)) return false;
+        if (!run_linear(c, l.fc1, &w.map_a, w.a, bf, M, w.g, tw.ff, c->use_gelu ? EPI_GELU16 : EPI_QGELU16, bf, 0, 1.f, &w.map_a_half, &w.map_out_g)) return false;
+        if (!run_linear(c, l.fc2, &w.map_g, w.g, bf, M, w.d, h, EPI_STORE16, bf, 0, 1.f, &w.map_g_half, &w.map_out_d)) return false;
         pending = true;
     }
     CK(cudaGetLastError());
@@ -1429,8 +1432,10 @@ int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int e
         else { if ((e = cudaMalloc(&d_w, wdev.size())) != cudaSuccess) { fail("malloc w", e); break; } cudaMemcpy(d_w, wdev.data(), wdev.size(), cudaMemcpyHostToDevice); }
         if (bias) { cudaMalloc(&d_bias, (size_t)N * 4); cudaMemcpy(d_bias, bias, (size_t)N * 4, cudaMemcpyHostToDevice); }
         cudaMemset(d_out, 0, out_bytes);
-        TmaMap xm, xh, wm;
+        TmaMap xm, xh, wm, om;
         memset(&wm, 0, sizeof(wm));
+        const bool use_out_map = !out32 && !(getenv("CLIP_B200_DEBUG_DIRECT_STORE") && atoi(getenv("CLIP_B200_DEBUG_DIRECT_STORE")) != 0);
+        if (use_out_map && !make_tma_2d_16bit_plain(&om, d_out, M, N, N, GEMM_OUT_BOX, GEMM_OUT_BOX)) { set_err("tensor map OUT failed"); rc = 4; break; }
         if (!make_tma_2d_16bit(&xm, d_x, M, K, K, GEMM_BN) || !make_tma_2d_16bit(&xh, d_x, M, K, K, GEMM_BN / 2)) { set_err("tensor map X failed"); rc = 4; break; }
         if (eff_q == QT_F16 && !make_tma_2d_16bit(&wm, d_w, N, K, K, GEMM_BM)) { set_err("tensor map W failed"); rc = 4; break; }
         cudaEventRecord(e0, st);
@@ -1441,7 +1446,7 @@ int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int e
             GemmArgs a;
             a.x_map = &xm; a.x_half_map = &xh; a.w_map = &wm; a.w_packed = (const uint8_t*)d_w; a.qtype = eff_q; a.operand_bf16 = operand_bf16 != 0;
             a.bias = d_bias; a.out = d_out; a.M = M; a.N = N; a.K = K; a.ldo = N; a.epi = epi; a.out_bf16 = operand_bf16;
-            a.scale_cols = N / 2; a.scale = 0.125f;
+            a.scale_cols = N / 2; a.scale = 0.125f; a.out_map = use_out_map ? &om : nullptr;
             e = gemm_launch(a, st, prop.multiProcessorCount, nullptr);
         }
         cudaEventRecord(e1, st);

@@ -58,6 +58,15 @@ CB_DEVINL void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 CB_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#ifdef CB_WAIT_HINT_NS     // experiment: let the hardware suspend the thread for up to this long instead of the system default
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"((uint32_t)CB_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -65,6 +74,7 @@ CB_DEVINL bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
@@ -136,6 +146,18 @@ CB_DEVINL void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, 
                  "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                  : "memory");
 }
+
+// TMA tensor STORE (shared -> global) with bulk-group completion: the issuing thread commits a group and later waits until the
+// group has finished READING shared memory before the staging buffer is reused.  Rows / columns outside the tensor map are clipped.
+CB_DEVINL void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(src_smem),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+CB_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+CB_DEVINL void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+CB_DEVINL void sts16(uint32_t a, uint16_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"(v) : "memory"); }
 
 // --------------------------------------------------------------------------------------------------
 // TMEM allocation (one warp, .sync.aligned) and loads

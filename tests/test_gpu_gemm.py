@@ -175,3 +175,46 @@ def test_gemm_large_persistent(prod):
     ref = expected(x, deq, None, True, EPI_STORE32, None, N)
     assert np.abs(y - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max())
     print("gemm %dx%dx%d q4_0: %.3f ms  %.1f TFLOP/s" % (M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
+
+
+@pytest.mark.parametrize("epi", [EPI_STORE16, EPI_QGELU16])
+def test_gemm_direct_store_epilogue_still_matches(prod, epi, monkeypatch):
+    """16-bit epilogues normally leave through shared memory + TMA store; the direct 2-byte store path (no output tensor map, e.g.
+    an output buffer the caller did not describe) must give the same bits."""
+    rng = np.random.default_rng(8)
+    M, N, K = 333, 256, 256
+    raw, deq = make_weight("q4_0", N, K, rng)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    a, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias)
+    monkeypatch.setenv("CLIP_B200_DEBUG_DIRECT_STORE", "1")
+    b, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("qt,bf16", [(qt, bf) for qt in ("q4_0", "q4_1", "q5_0", "q5_1", "q8_0") for bf in (True, False)])
+def test_gemm_wide_form_all_types(prod, qt, bf16):
+    """Enough [256 x 384] super-tiles for every CTA pair -> the WIDE kernel (both accumulators live, 8 UMMAs per A stage).  M is chosen
+    so that the last super-tile has a ragged first half only and the tail of the work list is walked as half items."""
+    rng = np.random.default_rng(21)
+    M, N, K = 37 * 384 + 100, 512, 128           # 2 feature-pair tiles x 38 super-tiles = 76 >= 74 pairs
+    raw, deq = make_weight(qt, N, K, rng)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    y, _ = run_gemm(prod, qt, bf16, M, N, K, EPI_STORE32, x, raw, bias)
+    ref = expected(x, deq, bias, bf16, EPI_STORE32, None, N)
+    assert np.abs(y - ref).max() <= 2e-3 * max(1.0, np.abs(ref).max()), (qt, bf16)
+
+
+@pytest.mark.parametrize("M", [74 * 384, 74 * 384 + 1, 75 * 384 - 191, 75 * 384 + 193, 111 * 384 + 7])
+@pytest.mark.parametrize("epi", [EPI_STORE16, EPI_QGELU16])
+def test_gemm_wide_form_tails_and_epilogues(prod, M, epi):
+    """wide kernel: exact multiples, one extra row, a lone first half, a ragged second half, 1.5 waves; 16-bit epilogues via TMA store"""
+    rng = np.random.default_rng(M)
+    N, K = 256, 192
+    raw, deq = make_weight("q4_0", N, K, rng)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    y, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias)
+    ref = expected(x, deq, bias, True, epi, None, N)
+    assert np.abs(y - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max())

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "clip.cpp_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import binding as bd, oracle as orc
 M, N, K = [int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (9252, 1024, 4096))]
-epi = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+epi = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 qt = int(sys.argv[5]) if len(sys.argv) > 5 else 2
 lib = bd.ClipLib()
 rng = np.random.default_rng(0)
@@ -21,7 +21,8 @@ for i in range(4):
     rc = lib.lib.clip_b200_debug_gemm(qt, 1, M, N, K, epi, 0, x.ctypes.data_as(fp), buf.ctypes.data, None, resid.ctypes.data_as(fp), y.ctypes.data_as(fp), C.byref(ms))
     assert rc == 0, lib.last_error()
     best = min(best, ms.value)
-tiles = (N // 128) * ((M + 191) // 192); kb = K // 64
-per_cta = -(-tiles // 148) * kb
+pair = (N % 256 == 0)
+tiles = (N // (256 if pair else 128)) * ((M + 191) // 192); kb = K // 64
+per_cta = -(-tiles // (74 if pair else 148)) * kb
 print("dbg=%s M=%d N=%d K=%d epi=%d qt=%d: %.1f us  %.0f TFLOP/s  ~%.0f cycles/k-block (%d k-blocks on the busiest CTA)" % (
     os.environ.get("CLIP_B200_GEMM_DBG", "0"), M, N, K, epi, qt, best * 1e3, 2.0 * M * N * K / best / 1e9, best * 1e-3 * 1.965e9 / per_cta, per_cta))
