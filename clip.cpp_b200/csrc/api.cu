@@ -659,7 +659,11 @@ void clip_image_f32_free(struct clip_image_f32* res) { clip_image_f32_clean(res)
 bool clip_image_load_from_file(const char* fname, struct clip_image_u8* img) {
     std::vector<uint8_t> rgb;
     int nx = 0, ny = 0;
-    if (!load_image_file(fname, rgb, nx, ny)) { fprintf(stderr, "%s: failed to load '%s' (PPM P6 / 24-bit BMP only)\n", __func__, fname); return false; }
+    if (!load_image_file(fname, rgb, nx, ny)) {
+        set_err(std::string("clip_image_load_from_file: cannot decode '") + fname + "': supported formats are PNG (non-interlaced, 8/16-bit), binary PPM (P6) and "
+                "24-bit BMP; JPEG / GIF are not decoded by this library (the reference uses stb_image, clip.cpp:709-726) -- convert first");
+        return false;
+    }
     img->nx = nx; img->ny = ny; img->size = rgb.size();
     img->data = new uint8_t[rgb.size()];
     memcpy(img->data, rgb.data(), rgb.size());

@@ -277,6 +277,15 @@ CB_DEVINL void umma_f16_ts_2sm_init(uint32_t tmem_d, uint32_t tmem_a, uint64_t d
         "r"(tmem_a), "l"(desc_b), "r"(idesc)
         : "memory");
 }
+// runtime accumulate flag (the first k-block of a tile overwrites D): one form for the unrolled issue loop of the pair kernel
+CB_DEVINL void umma_f16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 CB_DEVINL void umma_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
     const uint16_t mask = 3;
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)

@@ -70,6 +70,14 @@ struct Cfg {
     static_assert(XS % 1024 == 0, "stage alignment");
 };
 
+// Probe switches (KParams::dbg) exist only in experiment builds (make VARIANT=-DCB_GEMM_PROBE ...): the production kernels do not
+// carry their loads and branches in the issue loops.
+#ifdef CB_GEMM_PROBE
+#define CB_DBG(p, bit) ((p).dbg & (bit))
+#else
+#define CB_DBG(p, bit) 0
+#endif
+
 struct KParams {
     CUtensorMap tm_x;
     CUtensorMap tm_w;
@@ -268,7 +276,7 @@ CB_DEVINL void epilogue_tile(const KParams& p, uint32_t acc_addr, int tok0, int 
         uint32_t r[32];
         tmem_ld_32x32(acc_addr + c * 32, r);
         tmem_ld_wait();
-        if (p.dbg & 16) { if (r[0] == 0x7fc12345u && r[31] == 0x7fc54321u) reinterpret_cast<uint32_t*>(p.out)[0] = r[5]; }   // keep the loads alive
+        if (CB_DBG(p, 16)) { if (r[0] == 0x7fc12345u && r[31] == 0x7fc54321u) reinterpret_cast<uint32_t*>(p.out)[0] = r[5]; }   // keep the loads alive
         else if (nvalid >= 32) epilogue_chunk<EPI, BF, true>(p, r, off, ldo, 32, bias, mul);
         else epilogue_chunk<EPI, BF, false>(p, r, off, ldo, nvalid, bias, mul);
     }
@@ -338,12 +346,12 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                     const uint32_t dst = smem_base + s * C::XS;
                     if constexpr (PAIR) {
                         // both CTAs load their half of the token tile; all bytes are credited to the LEADER's x_full barrier
-                        if (p.dbg & 2) { if (leader) mbar_arrive(x_full + 8 * s); }
+                        if (CB_DBG(p, 2)) { if (leader) mbar_arrive(x_full + 8 * s); }
                         else {
                         if (leader) mbar_arrive_expect_tx(x_full + 8 * s, X_STAGE);
                         tma_load_2d_2sm(dst, &p.tm_xh, kb * BK, tt * BN + (int)rank * (BN / 2), mapa_rank0(x_full + 8 * s));
                         }
-                    } else if (p.dbg & 2) mbar_arrive(x_full + 8 * s);
+                    } else if (CB_DBG(p, 2)) mbar_arrive(x_full + 8 * s);
                     else {
                         mbar_arrive_expect_tx(x_full + 8 * s, C::XS);
                         tma_load_2d(dst, &p.tm_x, kb * BK, tt * BN, x_full + 8 * s);
@@ -364,7 +372,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 for (int kb = 0; kb < nkb; kb++) {
                     mbar_wait(q_empty + 8 * s, ph ^ 1);
                     if (elect_one()) {
-                        if (p.dbg & 4) mbar_arrive(q_full + 8 * s);
+                        if (CB_DBG(p, 4)) mbar_arrive(q_full + 8 * s);
                         else {
                         mbar_arrive_expect_tx(q_full + 8 * s, C::CHUNK);
                         bulk_load_1d(smem_base + C::Q_OFF + s * C::CHUNK, src + (size_t)kb * C::CHUNK, C::CHUNK, q_full + 8 * s);
@@ -381,9 +389,49 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
         const uint64_t dx0 = umma_desc_k128(smem_base);
         const uint64_t dw0 = umma_desc_k128(smem_base + X_STAGE);    // f16 path: W tile follows the X tile in each stage
         constexpr uint64_t X_STEP = C::XS >> 4;
+        if constexpr (PAIR) {
+            // The issuer is the serial heart of the kernel and shares its scheduler with an epilogue warp and two unpack warps: every
+            // instruction it does not execute is tensor time (tools/pipe_probe.cu: one busy ALU warp on its scheduler costs 25 %).  The
+            // ring walk is therefore unrolled over lcm(X ring, A ring) k-blocks: stage indices, barrier addresses and descriptor offsets
+            // are compile-time constants, the parities follow from the pass counter, and what remains per k-block is two barrier probes,
+            // four UMMAs and two or three commits.
+            constexpr int UNROLL = (SX % NA == 0) ? SX : (SX % 2 == 0 ? 2 * SX : 4 * SX);      // lcm(SX, 4)
+            static_assert(UNROLL % SX == 0 && UNROLL % NA == 0, "ring walk");
+            if (leader && elect_one()) {          // ONE thread runs the whole loop: no re-election, no reconvergence per k-block
+                const uint32_t total = (uint32_t)total_kb;
+                uint32_t i = 0, pass = 0, kb = 0, it = 0, d_tmem = tmem_base, as = 0;
+                while (i < total) {
+                    #pragma unroll
+                    for (int u = 0; u < UNROLL; u++) {
+                        if (i >= total) break;
+                        const int s = u % SX, sa = u % NA;
+                        if (kb == 0) {
+                            as = it & 1u;
+                            d_tmem = tmem_base + as * BN;
+                            mbar_wait(acc_empty + 8 * as, ((it >> 1) & 1u) ^ 1u);
+                        }
+                        mbar_wait(x_full + 8 * s, (((uint32_t)(UNROLL / SX) * pass) + (uint32_t)(u / SX)) & 1u);
+                        if (!CB_DBG(p, 64)) mbar_wait(a_full + 8 * sa, (((uint32_t)(UNROLL / NA) * pass) + (uint32_t)(u / NA)) & 1u);
+                        tc_fence_after();
+                        const uint64_t db = dx0 + (uint64_t)s * X_STEP;
+                        const uint32_t a_t = tmem_base + A_COL0 + sa * 32;
+                        umma_f16_ts_2sm(d_tmem, a_t, db, IDESC, kb);
+                        umma_f16_ts_2sm_acc(d_tmem, a_t + 8, db + 2, IDESC);
+                        umma_f16_ts_2sm_acc(d_tmem, a_t + 16, db + 4, IDESC);
+                        umma_f16_ts_2sm_acc(d_tmem, a_t + 24, db + 6, IDESC);
+                        umma_commit_2sm(x_empty + 8 * s);
+                        umma_commit_2sm(a_empty + 8 * sa);
+                        if (kb == (uint32_t)nkb - 1) umma_commit_2sm(acc_full + 8 * as);
+                        i++;
+                        if (++kb == (uint32_t)nkb) { kb = 0; it++; }
+                    }
+                    pass++;
+                }
+            }
+            __syncwarp();
+        } else {
         uint32_t s = 0, ph = 0, sa = 0, pa = 0;
         int it = 0;
-        if (leader)
         for (int tile = first; tile < n_tiles; tile += stride, it++) {
             const uint32_t as = it & 1, aph = (it >> 1) & 1;
             const uint32_t d_tmem = tmem_base + as * BN;
@@ -391,21 +439,11 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             tc_fence_after();
             for (int kb = 0; kb < nkb; kb++) {
                 mbar_wait(x_full + 8 * s, ph);
-                if constexpr (DQ) { if (!(p.dbg & 64)) mbar_wait(a_full + 8 * sa, pa); }
+                if constexpr (DQ) { if (!CB_DBG(p, 64)) mbar_wait(a_full + 8 * sa, pa); }
                 tc_fence_after();
                 const uint64_t db = dx0 + (uint64_t)s * X_STEP;
                 if (elect_one()) {
-                    if constexpr (PAIR) {
-                        const uint32_t a_t = tmem_base + A_COL0 + sa * 32;
-                        if (kb == 0) umma_f16_ts_2sm_init(d_tmem, a_t, db, IDESC);
-                        else umma_f16_ts_2sm_acc(d_tmem, a_t, db, IDESC);
-                        umma_f16_ts_2sm_acc(d_tmem, a_t + 8, db + 2, IDESC);
-                        umma_f16_ts_2sm_acc(d_tmem, a_t + 16, db + 4, IDESC);
-                        umma_f16_ts_2sm_acc(d_tmem, a_t + 24, db + 6, IDESC);
-                        umma_commit_2sm(x_empty + 8 * s);
-                        umma_commit_2sm(a_empty + 8 * sa);
-                        if (kb == nkb - 1) umma_commit_2sm(acc_full + 8 * as);
-                    } else if constexpr (DQ) {
+                    if constexpr (DQ) {
                         const uint32_t a_t = tmem_base + A_COL0 + sa * 32;      // 16 k = 8 TMEM columns per MMA step
                         if (kb == 0) umma_f16_ts_init(d_tmem, a_t, db, IDESC);
                         else umma_f16_ts_acc(d_tmem, a_t, db, IDESC);
@@ -423,12 +461,13 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                         umma_f16_acc(d_tmem, da + 6, db + 6, IDESC);
                         umma_commit(x_empty + 8 * s);
                     }
-                    if (!PAIR && kb == nkb - 1) umma_commit(acc_full + 8 * as);
+                    if (kb == nkb - 1) umma_commit(acc_full + 8 * as);
                 }
                 __syncwarp();
                 if (++s == SX) { s = 0; ph ^= 1; }
                 if constexpr (DQ) { if (++sa == NA) { sa = 0; pa ^= 1; } }
             }
+        }
         }
     } else if (warp >= 4 && warp < 8) {
         // ------------------------------------------------------------------ epilogue
@@ -437,7 +476,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
         int it = 0;
         uint32_t cidx = 0;
         const uint32_t out_stage = smem_base + C::OUT_OFF + (uint32_t)(warp & 3) * 4096u;
-        const bool tma_out = DQ && p.tma_out && !(p.dbg & 24);
+        const bool tma_out = DQ && p.tma_out && !(CB_DBG(p, 24));
         for (int tile = first; tile < n_tiles; tile += stride, it++) {
             const int ft = PAIR ? (tile % n_ft) * 2 + (int)rank : tile % n_ft, tt = tile / n_ft;
             const uint32_t as = it & 1, aph = (it >> 1) & 1;
@@ -456,7 +495,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 default: epilogue_tile_tma<EPI_STORE16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                 }
             } else
-            if (!(p.dbg & 8)) switch (p.epi) {
+            if (!(CB_DBG(p, 8))) switch (p.epi) {
             case EPI_STORE16: epilogue_tile<EPI_STORE16, BF>(p, acc_addr, tok0, n, bias, mul); break;
             case EPI_GELU16: epilogue_tile<EPI_GELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
             case EPI_QGELU16: epilogue_tile<EPI_QGELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
@@ -480,15 +519,15 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 mbar_wait(q_full + 8 * qs, qph);
                 const uint32_t qa = smem_base + C::Q_OFF + qs * C::CHUNK;
                 uint32_t v[32];
-                if (!(p.dbg & 1)) {
+                if (!(CB_DBG(p, 1))) {
                     unpack_block<DQ ? QT : QT_Q4_0, BF>(qa, row, v);              // k  0..31 of this row
                     unpack_block<DQ ? QT : QT_Q4_0, BF>(qa, 128 + row, v + 16);   // k 32..63
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(q_empty + 8 * qs);
-                if (!(p.dbg & 32)) mbar_wait(a_empty + 8 * sa, pa ^ 1);
+                if (!(CB_DBG(p, 32))) mbar_wait(a_empty + 8 * sa, pa ^ 1);
                 tc_fence_after();
-                if (!(p.dbg & 1)) {
+                if (!(CB_DBG(p, 1))) {
                     tmem_st_32x32(a_lane + sa * 32, v);
                     tmem_st_wait();
                 }
@@ -580,7 +619,7 @@ __global__ void __launch_bounds__(512, 1) gemm_dq2_kernel(const __grid_constant_
                 for (int h = 0; h < w.nh; h++) {
                     mbar_wait(x_empty + 8 * s, ph ^ 1);
                     if (elect_one()) {
-                        if (p.dbg & 2) { if (leader) mbar_arrive(x_full + 8 * s); }
+                        if (CB_DBG(p, 2)) { if (leader) mbar_arrive(x_full + 8 * s); }
                         else {
                             if (leader) mbar_arrive_expect_tx(x_full + 8 * s, X_STAGE);
                             tma_load_2d_2sm(smem_base + s * C::XS, &p.tm_xh, kb * BK, w.tok0 + h * BN + (int)rank * (BN / 2), mapa_rank0(x_full + 8 * s));
@@ -599,7 +638,7 @@ __global__ void __launch_bounds__(512, 1) gemm_dq2_kernel(const __grid_constant_
             for (int kb = 0; kb < nkb; kb++) {
                 mbar_wait(q_empty + 8 * s, ph ^ 1);
                 if (elect_one()) {
-                    if (p.dbg & 4) mbar_arrive(q_full + 8 * s);
+                    if (CB_DBG(p, 4)) mbar_arrive(q_full + 8 * s);
                     else {
                         mbar_arrive_expect_tx(q_full + 8 * s, C::CHUNK);
                         bulk_load_1d(smem_base + C::Q_OFF + s * C::CHUNK, src + (size_t)kb * C::CHUNK, C::CHUNK, q_full + 8 * s);
@@ -619,7 +658,7 @@ __global__ void __launch_bounds__(512, 1) gemm_dq2_kernel(const __grid_constant_
                 if (w.nh == 0) continue;
                 mbar_wait(acc_empty + 0, (u0 & 1) ^ 1);
                 for (int kb = 0; kb < nkb; kb++) {
-                    if (!(p.dbg & 64)) mbar_wait(a_full + 8 * sa, pa);
+                    if (!(CB_DBG(p, 64))) mbar_wait(a_full + 8 * sa, pa);
                     const uint32_t a_t = tmem_base + A_COL0 + sa * 32;
                     for (int h = 0; h < w.nh; h++) {
                         mbar_wait(x_full + 8 * s, ph);
@@ -652,7 +691,7 @@ __global__ void __launch_bounds__(512, 1) gemm_dq2_kernel(const __grid_constant_
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t cidx = 0, u0 = 0, u1 = 0;
         const uint32_t out_stage = smem_base + C::OUT_OFF + (uint32_t)(warp & 3) * 4096u;
-        const bool tma_out = p.tma_out && !(p.dbg & 24);
+        const bool tma_out = p.tma_out && !(CB_DBG(p, 24));
         for (int g = first; get_work(g, n_ft, n_super, full, p.M, w); g += stride) {
             if (w.nh == 0) continue;
             const int ft = w.ft * 2 + (int)rank;
@@ -671,7 +710,7 @@ __global__ void __launch_bounds__(512, 1) gemm_dq2_kernel(const __grid_constant_
                     case EPI_QGELU16: epilogue_tile_tma<EPI_QGELU16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                     default: epilogue_tile_tma<EPI_STORE16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                     }
-                } else if (!(p.dbg & 8)) switch (p.epi) {
+                } else if (!(CB_DBG(p, 8))) switch (p.epi) {
                 case EPI_STORE16: epilogue_tile<EPI_STORE16, BF>(p, acc_addr, tok0, n, bias, mul); break;
                 case EPI_GELU16: epilogue_tile<EPI_GELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
                 case EPI_QGELU16: epilogue_tile<EPI_QGELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
@@ -699,15 +738,15 @@ __global__ void __launch_bounds__(512, 1) gemm_dq2_kernel(const __grid_constant_
             mbar_wait(q_full + 8 * qs, qph);
             const uint32_t qa = smem_base + C::Q_OFF + qs * C::CHUNK;
             uint32_t v[32];
-            if (!(p.dbg & 1)) {
+            if (!(CB_DBG(p, 1))) {
                 unpack_block<QT, BF>(qa, row, v);
                 unpack_block<QT, BF>(qa, 128 + row, v + 16);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(q_empty + 8 * qs);
-            if (!(p.dbg & 32)) mbar_wait(a_empty + 8 * sa, pa ^ 1);
+            if (!(CB_DBG(p, 32))) mbar_wait(a_empty + 8 * sa, pa ^ 1);
             tc_fence_after();
-            if (!(p.dbg & 1)) {
+            if (!(CB_DBG(p, 1))) {
                 tmem_st_32x32(a_lane + sa * 32, v);
                 tmem_st_wait();
             }
@@ -834,8 +873,10 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream, int num_sms, uin
     const int grid = n_tiles < num_sms ? n_tiles : num_sms;
     if (launches) ++*launches;
     static const bool pair_off = getenv("CLIP_B200_GEMM_PAIR") && atoi(getenv("CLIP_B200_GEMM_PAIR")) == 0;
-    static const bool wide_off = getenv("CLIP_B200_GEMM_WIDE") && atoi(getenv("CLIP_B200_GEMM_WIDE")) == 0;
-    if (a.x_half_map && !pair_off && !wide_off && a.qtype != QT_F16 && a.N % (2 * BM) == 0) {
+    // the wide form measured SLOWER than the double-buffered pair form on every layer shape (profiles/r02_gemm_wide.md: its exposed
+    // epilogue costs more than the halved unpack work returns); kept selectable for experiments, off by default
+    const bool wide_on = getenv("CLIP_B200_GEMM_WIDE") && atoi(getenv("CLIP_B200_GEMM_WIDE")) != 0;
+    if (a.x_half_map && !pair_off && wide_on && a.qtype != QT_F16 && a.N % (2 * BM) == 0) {
         // wide form: [256 x 384] super-tiles; worth it once every pair gets at least one of them
         const int n_super = (a.N / (2 * BM)) * ((a.M + 2 * BN - 1) / (2 * BN));
         int pairs = num_sms / 2;

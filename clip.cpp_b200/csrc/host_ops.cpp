@@ -10,6 +10,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <zlib.h>
+
 #include <algorithm>
 #include <fstream>
 
@@ -388,10 +390,73 @@ bool quantize_file(const char* inp, const char* outp, int itype, std::string& er
 // image files: binary PPM (P6, maxval 255) and 24-bit uncompressed BMP.  (The reference uses stb_image,
 // clip.cpp:709-726; JPEG/PNG decoding is host-side convenience outside the hot path and is not reproduced.)
 // ---------------------------------------------------------------------------------------------------
+// PNG (the lossless format the reference's callers use besides JPEG; the reference decodes through stb_image, clip.cpp:709-726, and asks
+// for 3 channels: alpha is dropped, grey is replicated, 16-bit samples keep their high byte).  Non-interlaced, colour types 0/2/3/4/6,
+// 8 or 16 bits per sample (palette: 8).  zlib does the inflate; the result is bit-identical to what stb_image returns.
+static bool decode_png(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rgb, int& nx, int& ny) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (buf.size() < 8 + 25 || memcmp(buf.data(), sig, 8) != 0) return false;
+    auto be32 = [&](size_t o) { return ((uint32_t)buf[o] << 24) | ((uint32_t)buf[o + 1] << 16) | ((uint32_t)buf[o + 2] << 8) | buf[o + 3]; };
+    uint32_t w = 0, h = 0;
+    int depth = 0, ctype = -1, interlace = 0;
+    std::vector<uint8_t> idat, pal;
+    for (size_t p = 8; p + 12 <= buf.size();) {
+        const uint32_t len = be32(p);
+        if (len > buf.size() - p - 12) return false;
+        const uint8_t* tag = &buf[p + 4];
+        const uint8_t* d = &buf[p + 8];
+        if (!memcmp(tag, "IHDR", 4) && len >= 13) { w = be32(p + 8); h = be32(p + 12); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+        else if (!memcmp(tag, "PLTE", 4)) pal.assign(d, d + len);
+        else if (!memcmp(tag, "IDAT", 4)) idat.insert(idat.end(), d, d + len);
+        else if (!memcmp(tag, "IEND", 4)) break;
+        p += 12 + (size_t)len;
+    }
+    if (w == 0 || h == 0 || w > 65535 || h > 65535 || interlace != 0) return false;
+    int ch;
+    switch (ctype) { case 0: ch = 1; break; case 2: ch = 3; break; case 3: ch = 1; break; case 4: ch = 2; break; case 6: ch = 4; break; default: return false; }
+    if (!(depth == 8 || (depth == 16 && ctype != 3))) return false;
+    const size_t bps = (size_t)depth / 8, bpp = bps * ch, stride = bpp * w;
+    std::vector<uint8_t> raw((stride + 1) * h);
+    uLongf got = (uLongf)raw.size();
+    if (uncompress(raw.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != raw.size()) return false;
+    std::vector<uint8_t> prev(stride, 0), cur(stride);
+    rgb.resize((size_t)w * h * 3);
+    for (uint32_t y = 0; y < h; y++) {
+        const uint8_t ft = raw[(stride + 1) * y];
+        const uint8_t* in = &raw[(stride + 1) * y + 1];
+        for (size_t i = 0; i < stride; i++) {
+            const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+            int pred;
+            switch (ft) {
+            case 0: pred = 0; break;
+            case 1: pred = a; break;
+            case 2: pred = b; break;
+            case 3: pred = (a + b) >> 1; break;
+            case 4: { const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); } break;
+            default: return false;
+            }
+            cur[i] = (uint8_t)(in[i] + pred);
+        }
+        uint8_t* out = &rgb[(size_t)y * w * 3];
+        for (uint32_t x = 0; x < w; x++) {
+            const uint8_t* px = &cur[x * bpp];          // 16-bit samples are big-endian: the first byte is the high byte stb keeps
+            switch (ctype) {
+            case 0: case 4: out[3 * x] = out[3 * x + 1] = out[3 * x + 2] = px[0]; break;
+            case 2: case 6: out[3 * x] = px[0]; out[3 * x + 1] = px[bps]; out[3 * x + 2] = px[2 * bps]; break;
+            case 3: { const size_t k = (size_t)px[0] * 3; if (k + 3 > pal.size()) return false; out[3 * x] = pal[k]; out[3 * x + 1] = pal[k + 1]; out[3 * x + 2] = pal[k + 2]; } break;
+            }
+        }
+        prev.swap(cur);
+    }
+    nx = (int)w; ny = (int)h;
+    return true;
+}
+
 bool load_image_file(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny) {
     std::ifstream f(fname, std::ios::binary);
     if (!f) return false;
     std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    if (buf.size() >= 8 && buf[0] == 0x89 && buf[1] == 'P' && buf[2] == 'N' && buf[3] == 'G') return decode_png(buf, rgb, nx, ny);
     if (buf.size() >= 2 && buf[0] == 'P' && buf[1] == '6') {
         size_t p = 2;
         int vals[3], got = 0;

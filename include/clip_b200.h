@@ -111,8 +111,9 @@ void clip_image_f32_clean(struct clip_image_f32 * res);
 void clip_image_u8_free(struct clip_image_u8 * img);
 void clip_image_f32_free(struct clip_image_f32 * res);
 
-/* clip.h:87, clip.cpp:709-726 -- the reference decodes with stb_image; this library reads binary PPM (P6) and
- * uncompressed BMP only and returns false for other formats (decoding is outside the hot path) */
+/* clip.h:87, clip.cpp:709-726 -- the reference decodes with stb_image; this library decodes PNG (non-interlaced, 8 / 16 bits per
+ * sample, bit-identical to stb_image's 3-channel output), binary PPM (P6) and 24-bit BMP.  JPEG / GIF return false with an explicit
+ * message in clip_b200_last_error (decoding is outside the hot path). */
 bool clip_image_load_from_file(const char * fname, struct clip_image_u8 * img);
 
 /* clip.h:88, clip.cpp:797-927 -- host side PIL-style bicubic resize + centre crop + normalise */

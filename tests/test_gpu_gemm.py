@@ -193,9 +193,10 @@ def test_gemm_direct_store_epilogue_still_matches(prod, epi, monkeypatch):
 
 
 @pytest.mark.parametrize("qt,bf16", [(qt, bf) for qt in ("q4_0", "q4_1", "q5_0", "q5_1", "q8_0") for bf in (True, False)])
-def test_gemm_wide_form_all_types(prod, qt, bf16):
+def test_gemm_wide_form_all_types(prod, qt, bf16, monkeypatch):
     """Enough [256 x 384] super-tiles for every CTA pair -> the WIDE kernel (both accumulators live, 8 UMMAs per A stage).  M is chosen
     so that the last super-tile has a ragged first half only and the tail of the work list is walked as half items."""
+    monkeypatch.setenv("CLIP_B200_GEMM_WIDE", "1")
     rng = np.random.default_rng(21)
     M, N, K = 37 * 384 + 100, 512, 128           # 2 feature-pair tiles x 38 super-tiles = 76 >= 74 pairs
     raw, deq = make_weight(qt, N, K, rng)
@@ -208,8 +209,9 @@ def test_gemm_wide_form_all_types(prod, qt, bf16):
 
 @pytest.mark.parametrize("M", [74 * 384, 74 * 384 + 1, 75 * 384 - 191, 75 * 384 + 193, 111 * 384 + 7])
 @pytest.mark.parametrize("epi", [EPI_STORE16, EPI_QGELU16])
-def test_gemm_wide_form_tails_and_epilogues(prod, M, epi):
+def test_gemm_wide_form_tails_and_epilogues(prod, M, epi, monkeypatch):
     """wide kernel: exact multiples, one extra row, a lone first half, a ragged second half, 1.5 waves; 16-bit epilogues via TMA store"""
+    monkeypatch.setenv("CLIP_B200_GEMM_WIDE", "1")
     rng = np.random.default_rng(M)
     N, K = 256, 192
     raw, deq = make_weight("q4_0", N, K, rng)

@@ -120,3 +120,47 @@ def test_scoring_helpers_match_reference_arithmetic(prod):
     assert np.array_equal(idx, np.argsort(-p, kind="stable"))
     assert np.allclose(scores, p[idx], rtol=1e-6)
     assert not prod.lib.softmax_with_sorting(arr.ctypes.data_as(fp), 0, scores.ctypes.data_as(fp), idx.ctypes.data_as(C.POINTER(C.c_int)))
+
+
+def _load_file(lib, path):
+    lib.lib.clip_image_load_from_file.restype = C.c_bool
+    lib.lib.clip_image_load_from_file.argtypes = [C.c_char_p, C.POINTER(bd.clip_image_u8)]
+    im = bd.clip_image_u8()
+    if not lib.lib.clip_image_load_from_file(path.encode(), C.byref(im)):
+        return None
+    return np.ctypeslib.as_array(im.data, shape=(im.ny, im.nx, 3)).copy()
+
+
+def test_png_decode_matches_pil_and_rejects_jpeg(prod, tmp_path):
+    """clip_image_load_from_file (clip.cpp:709-726): PNG of every colour type decodes to the 3-channel pixels stb_image / PIL give;
+    JPEG is refused with an explicit message instead of garbage."""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
+    files = {"rgb.png": Image.fromarray(rgb), "rgba.png": Image.fromarray(rng.integers(0, 256, (20, 31, 4), dtype=np.uint8), "RGBA"),
+             "gray.png": Image.fromarray(rng.integers(0, 256, (20, 31), dtype=np.uint8), "L"),
+             "pal.png": Image.fromarray(rgb).convert("P", palette=Image.ADAPTIVE)}
+    for name, im in files.items():
+        p = str(tmp_path / name)
+        im.save(p, optimize=(name == "rgb.png"))
+        got = _load_file(prod, p)
+        assert got is not None, (name, prod.last_error())
+        assert np.array_equal(got, np.array(Image.open(p).convert("RGB"))), name
+    j = str(tmp_path / "x.jpg")
+    Image.fromarray(rgb).save(j)
+    assert _load_file(prod, j) is None and b"JPEG" in prod.lib.clip_b200_last_error()
+
+
+@pytest.mark.skipif(not ref_run.available(), reason="oracle/_ref not built")
+def test_png_decode_matches_live_reference(prod, tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(1)
+    ref = bd.ClipLib(ref_run.REF_LIB)
+    ims = {"g16.png": Image.fromarray(rng.integers(0, 65536, (11, 13), dtype=np.uint16)),
+           "la.png": Image.fromarray(rng.integers(0, 256, (20, 31, 2), dtype=np.uint8), "LA"),
+           "rgb.png": Image.fromarray(rng.integers(0, 256, (64, 48, 3), dtype=np.uint8))}
+    for name, im in ims.items():
+        p = str(tmp_path / name)
+        im.save(p)
+        a, b = _load_file(prod, p), _load_file(ref, p)
+        assert a is not None and b is not None and np.array_equal(a, b), name
