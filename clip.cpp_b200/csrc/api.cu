@@ -240,7 +240,7 @@ bool ensure_ws(clip_ctx* c, Tower& tw, int items, int T, bool vision) {
     bool ok = make_tma_2d_16bit(&w.map_a, w.a, rows, h, h, GEMM_BN) && make_tma_2d_16bit(&w.map_g, w.g, rows, tw.ff, tw.ff, GEMM_BN) &&
               make_tma_2d_16bit(&w.map_sel, w.sel16, items, h, h, GEMM_BN) &&
               make_tma_2d_16bit(&w.map_a_half, w.a, rows, h, h, GEMM_BN / 2) && make_tma_2d_16bit(&w.map_g_half, w.g, rows, tw.ff, tw.ff, GEMM_BN / 2) &&
-              make_tma_2d_16bit(&w.map_q128, w.qkv, rows, 3 * h, 3 * h, 128) && make_tma_2d_16bit(&w.map_kv256, w.qkv, rows, 3 * h, 3 * h, 256) &&
+              make_tma_2d_16bit(&w.map_q128, w.qkv, rows, 3 * h, 3 * h, 128) &&
               make_tma_2d_16bit(&w.map_kv16, w.qkv, rows, 3 * h, 3 * h, 16) &&
               make_tma_2d_16bit_plain(&w.map_out_qkv, w.qkv, rows, 3 * h, 3 * h, GEMM_OUT_BOX, GEMM_OUT_BOX) &&
               make_tma_2d_16bit_plain(&w.map_out_d, w.d, rows, h, h, GEMM_OUT_BOX, GEMM_OUT_BOX) &&
@@ -287,7 +287,7 @@ bool run_blocks(clip_ctx* c, Tower& tw, int nseq, int T, bool causal) {
         if (!run_linear(c, l.qkv, &w.map_a, w.a, bf, M, w.qkv, 3 * h, EPI_STORE16, bf, h, qscale, &w.map_a_half, &w.map_out_qkv)) return false;
         if (c->attn_tc && attention_tc_supported(T)) {
             const int q_done = attention_tc_tiles(T) * 128;
-            { Scope s(c, K_ATTN); CK(launch_attention_tc(&w.map_q128, &w.map_kv256, &w.map_kv16, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, c->num_sms, c->stream)); }
+            { Scope s(c, K_ATTN); CK(launch_attention_tc(&w.map_q128, w.qkv, &w.map_kv16, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, c->num_sms, c->stream)); }
             if (q_done < T) { Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, q_done, c->stream); }
         } else {
             Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, 0, c->stream);
@@ -1500,13 +1500,13 @@ int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int caus
         cudaMemset(d_out, 0xff, rows * hid * 2);
         cudaMemcpy(d_qkv, h16.data(), h16.size() * 2, cudaMemcpyHostToDevice);
         cudaStreamCreate(&st); cudaEventCreate(&e0); cudaEventCreate(&e1);
-        TmaMap mq, mkv, m16;
-        if (!make_tma_2d_16bit(&mq, d_qkv, rows, 3 * hid, 3 * hid, 128) || !make_tma_2d_16bit(&mkv, d_qkv, rows, 3 * hid, 3 * hid, 256) ||
+        TmaMap mq, m16;
+        if (!make_tma_2d_16bit(&mq, d_qkv, rows, 3 * hid, 3 * hid, 128) ||
             !make_tma_2d_16bit(&m16, d_qkv, rows, 3 * hid, 3 * hid, 16)) { set_err("tensor map failed"); rc = 4; break; }
         for (int rep = 0; rep < (ms ? 3 : 1); rep++) {
             cudaEventRecord(e0, st);
             if (use_legacy) { launch_attention(d_qkv, d_out, nseq, T, H, causal, operand_bf16, 0, st); e = cudaGetLastError(); }
-            else e = launch_attention_tc(&mq, &mkv, &m16, d_out, nseq, T, H, causal, operand_bf16, prop.multiProcessorCount, st);
+            else e = launch_attention_tc(&mq, d_qkv, &m16, d_out, nseq, T, H, causal, operand_bf16, prop.multiProcessorCount, st);
             cudaEventRecord(e1, st);
             if (e != cudaSuccess) break;
             if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;

@@ -61,6 +61,12 @@ CB_DEVINL void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
         "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+CB_DEVINL void tma_load_3d(uint32_t dst_smem, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst_smem),
+        "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 CB_DEVINL float ex2f(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 template <bool BF>
 CB_DEVINL uint32_t pack2(float lo, float hi) {
@@ -159,8 +165,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             mbar_wait(kv_empty + 8 * st, ((i >> 1) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(kv_full + 8 * st, 2 * kv_tx);
-                tma_load_2d(k_s, &p.tm_kv256, hid + c, row0, kv_full + 8 * st);
-                tma_load_2d(v_s, &p.tm_kv256, 2 * hid + c, row0, kv_full + 8 * st);
+                // 3-D view [sequence][token][column]: rows past THIS sequence's T tokens are out of bounds and arrive as zeros, so the
+                // padded keys of the P.V product can never pick up another sequence's (or stale) NaN / Inf through 0 * x
+                tma_load_3d(k_s, &p.tm_kv256, hid + c, 0, seq, kv_full + 8 * st);
+                tma_load_3d(v_s, &p.tm_kv256, 2 * hid + c, 0, seq, kv_full + 8 * st);
                 if (extra) {
                     tma_load_2d(k_s + 32768, &p.tm_kv16, hid + c, row0 + 256, kv_full + 8 * st);
                     tma_load_2d(v_s + 32768, &p.tm_kv16, 2 * hid + c, row0 + 256, kv_full + 8 * st);
@@ -188,8 +196,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer.  S(g+1) is issued BEFORE P.V(g): the
         // tensor core computes the next score tile while softmax group g&1 is busy, and the two groups keep the MUFU pipe fed.
+        // ONE elected thread runs the whole issue loop (no re-election / reconvergence per tile): the issuer shares its scheduler with
+        // four softmax warps, and every instruction it does not execute shortens the S -> softmax -> P.V chain (same finding as K1's issuer)
         const uint32_t id_s = idesc_n(BF, nmma, false), id_pv = idesc_n(BF, DH, true);
         const int npv = nmma >> 4;
+        if (elect_one()) {
         auto issue_s = [&](int g) {
             const uint32_t sl = g & 1, u = (g >> 1) & 1;
             const int i = g / ntile, qt = g - i * ntile;
@@ -197,48 +208,33 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             mbar_wait(q_full + 8 * sl, u);
             mbar_wait(s_free + 8 * sl, u ^ 1);          // the epilogue of tile g-2 has read O out of this TMEM buffer
             tc_fence_after();
-            if (elect_one()) {
-                const uint64_t dq = umma_desc_k128(smem_base + Q_OFF + sl * Q_BYTES), dk = umma_desc_k128(smem_base + (i & 1) * (2 * KV_BYTES));
-                const uint32_t d = tmem_base + sl * S_COLS;
-                umma_f16_init(d, dq, dk, id_s);
-                umma_f16_acc(d, dq + 2, dk + 2, id_s);
-                umma_f16_acc(d, dq + 4, dk + 4, id_s);
-                umma_f16_acc(d, dq + 6, dk + 6, id_s);
-                umma_commit(s_full + 8 * sl);
-            }
-            __syncwarp();
+            const uint64_t dq = umma_desc_k128(smem_base + Q_OFF + sl * Q_BYTES), dk = umma_desc_k128(smem_base + (i & 1) * (2 * KV_BYTES));
+            const uint32_t d = tmem_base + sl * S_COLS;
+            umma_f16_init(d, dq, dk, id_s);
+            umma_f16_acc(d, dq + 2, dk + 2, id_s);
+            umma_f16_acc(d, dq + 4, dk + 4, id_s);
+            umma_f16_acc(d, dq + 6, dk + 6, id_s);
+            umma_commit(s_full + 8 * sl);
         };
         if (G > 0) issue_s(0);
         for (int g = 0; g < G; g++) {
             if (g + 1 < G) issue_s(g + 1);
             const uint32_t sl = g & 1;
             const int i = g / ntile;
-            if (g == i * ntile && p.T < nmma) {
-                // V rows of the padded keys [T, nmma) belong to the NEXT sequence (or lie past the last one, where the buffer holds
-                // whatever was there before): their probabilities are exactly 0, but 0 * NaN/Inf would still poison every output row
-                // of this item.  Zero them once per K/V stage (a 128-B swizzled row stays inside its own 128 bytes), then make the
-                // generic-proxy stores visible to the UMMA operand reads.
-                const uint32_t v0 = smem_base + (i & 1) * (2 * KV_BYTES) + KV_BYTES + (uint32_t)p.T * 128;
-                for (int c = lane; c < (nmma - p.T) * 8; c += 32)
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(v0 + 16 * c), "r"(0u) : "memory");
-                fence_proxy_async_smem();
-                __syncwarp();
-            }
             mbar_wait(p_full + 8 * sl, (g >> 1) & 1);
             tc_fence_after();
-            if (elect_one()) {
-                const uint64_t dv = umma_desc_mn128(smem_base + (i & 1) * (2 * KV_BYTES) + KV_BYTES);
-                const uint32_t pa = tmem_base + sl * S_COLS, d = pa + O_COL;
-                for (int ks = 0; ks < npv; ks++) {     // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2048 B) of V
-                    const int c = ks >> 1;
-                    const uint32_t pcol = (c < nch_a ? 16 * c : 32 * nch_a + 16 * (c - nch_a)) + 8 * (ks & 1);
-                    if (ks == 0) umma_f16_ts_init(d, pa + pcol, dv, id_pv);
-                    else umma_f16_ts_acc(d, pa + pcol, dv + (uint64_t)ks * (2048 >> 4), id_pv);
-                }
-                umma_commit(o_full + 8 * sl);
+            const uint64_t dv = umma_desc_mn128(smem_base + (i & 1) * (2 * KV_BYTES) + KV_BYTES);
+            const uint32_t pa = tmem_base + sl * S_COLS, d = pa + O_COL;
+            for (int ks = 0; ks < npv; ks++) {     // 16 keys per step: 8 packed TMEM columns of P, 16 rows (2048 B) of V
+                const int c = ks >> 1;
+                const uint32_t pcol = (c < nch_a ? 16 * c : 32 * nch_a + 16 * (c - nch_a)) + 8 * (ks & 1);
+                if (ks == 0) umma_f16_ts_init(d, pa + pcol, dv, id_pv);
+                else umma_f16_ts_acc(d, pa + pcol, dv + (uint64_t)ks * (2048 >> 4), id_pv);
             }
-            __syncwarp();
+            umma_commit(o_full + 8 * sl);
         }
+        }
+        __syncwarp();
     } else if (warp < 4) {
         // ------------------------------------------------------------------ last query row (T % 128 == 1, e.g. row 256 of a
         // ViT-L/14 sequence) on the CUDA cores: warp 2 takes the even items of this CTA, warp 3 the odd ones
@@ -481,12 +477,33 @@ cudaError_t attention_tc_init() {
     return cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
 }
 
-cudaError_t launch_attention_tc(const TmaMap* map_q, const TmaMap* map_kv256, const TmaMap* map_kv16, void* out16, int nseq, int T,
+typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// [nseq][T][3*H*64] view of the fused QKV activations, box = 64 columns x 256 tokens x 1 sequence (128-byte swizzle, zero fill)
+static bool make_kv_map(CUtensorMap* out, const void* qkv16, int nseq, int T, int H) {
+    static EncodeTiledFn3 enc = nullptr;
+    if (!enc) {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return false;
+        enc = reinterpret_cast<EncodeTiledFn3>(f);
+    }
+    const cuuint64_t cols = (cuuint64_t)3 * H * DH;
+    const cuuint64_t dims[3] = {cols, (cuuint64_t)T, (cuuint64_t)nseq};
+    const cuuint64_t strides[2] = {cols * 2, cols * 2 * (cuuint64_t)T};
+    const cuuint32_t box[3] = {64, 256, 1}, estr[3] = {1, 1, 1};
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(qkv16), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+cudaError_t launch_attention_tc(const TmaMap* map_q, const void* qkv16, const TmaMap* map_kv16, void* out16, int nseq, int T,
                                 int H, int causal, int bf16, int num_sms, cudaStream_t st) {
     if (nseq <= 0) return cudaSuccess;
     AParams p;
     memcpy(&p.tm_q, map_q, sizeof(CUtensorMap));
-    memcpy(&p.tm_kv256, map_kv256, sizeof(CUtensorMap));
+    if (!make_kv_map(&p.tm_kv256, qkv16, nseq, T, H)) return cudaErrorInvalidValue;
     memcpy(&p.tm_kv16, map_kv16, sizeof(CUtensorMap));
     p.out = (uint16_t*)out16; p.T = T; p.H = H; p.nseq = nseq; p.causal = causal;
     p.last_row = (T > 1 && T % AQ == 1) ? 1 : 0;      // e.g. 257 = 2 tensor-core tiles + one row on the CUDA cores

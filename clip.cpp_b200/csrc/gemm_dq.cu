@@ -403,9 +403,9 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 while (i < total) {
                     #pragma unroll
                     for (int u = 0; u < UNROLL; u++) {
-                        if (i >= total) break;
                         const int s = u % SX, sa = u % NA;
                         if (kb == 0) {
+                            if (i >= total) break;                 // the work list ends on a tile boundary
                             as = it & 1u;
                             d_tmem = tmem_base + as * BN;
                             mbar_wait(acc_empty + 8 * as, ((it >> 1) & 1u) ^ 1u);

@@ -29,13 +29,14 @@ void launch_text_embed(const int32_t* ids, const float* tok, const float* pos, i
 // q_start (multiple of 64): first query row this launch computes (rows before it come from the tcgen05 kernel below).
 void launch_attention(const void* qkv16, void* out16, int nseq, int T, int H, int causal, int bf16, int q_start, cudaStream_t st);
 
-// K3 on tcgen05 (attention_tc.cu): 128-query tiles, S and O accumulators in TMEM.  Maps are TMA views of the qkv matrix
-// [rows, 3*H*64] with box rows 128 / 256 / 16.  Handles query tiles [0, attention_tc_tiles(T)); T must satisfy _supported().
+// K3 on tcgen05 (attention_tc.cu): 128-query tiles, S and O accumulators in TMEM.  map_q / map_kv16 are TMA views of the qkv matrix
+// [rows, 3*H*64] with box rows 128 / 16; the K / V boxes come from a per-launch 3-D view [sequence][token][column] of qkv16 (zero fill
+// past each sequence's T tokens).  Handles query tiles [0, attention_tc_tiles(T)); T must satisfy _supported().
 struct TmaMap;
 bool attention_tc_supported(int T);
 int attention_tc_tiles(int T);
 cudaError_t attention_tc_init();
-cudaError_t launch_attention_tc(const TmaMap* map_q, const TmaMap* map_kv256, const TmaMap* map_kv16, void* out16, int nseq, int T,
+cudaError_t launch_attention_tc(const TmaMap* map_q, const void* qkv16, const TmaMap* map_kv16, void* out16, int nseq, int T,
                                 int H, int causal, int bf16, int num_sms, cudaStream_t st);
 
 // K5 head tail: out[r,:] = normalize ? v / sqrt(sum v^2) : v    (clip.cpp:1163-1166, 1448-1455)

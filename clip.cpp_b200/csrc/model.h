@@ -47,7 +47,7 @@ struct Workspace {
     int32_t* last = nullptr;     // index of the EOT row per sequence (len - 1)
     TmaMap map_a, map_g, map_patches, map_sel;
     TmaMap map_a_half, map_g_half;          // box of GEMM_BN/2 tokens: B-operand halves of the CTA-pair GEMM
-    TmaMap map_q128, map_kv256, map_kv16;   // views of qkv for the tcgen05 attention kernel
+    TmaMap map_q128, map_kv16;              // views of qkv for the tcgen05 attention kernel (K / V: per-launch 3-D view)
     TmaMap map_out_qkv, map_out_d, map_out_g;   // plain 32 x 32 boxes: TMA-store targets of the GEMM epilogue
 };
 
