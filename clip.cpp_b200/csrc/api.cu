@@ -234,7 +234,7 @@ bool ensure_ws(clip_ctx* c, Tower& tw, int items, int T, bool vision) {
     const int h = tw.hidden;
     w.cap_items = items; w.T = T; w.cap_rows = items * T;
     const size_t rows = (size_t)w.cap_rows;
-    if (!dev_alloc(c, &w.x, rows * h) || !dev_alloc(c, &w.a, rows * h) || !dev_alloc(c, &w.d, rows * h) || !dev_alloc(c, &w.qkv, rows * 3 * h) ||
+    if (!dev_alloc(c, &w.x, rows * h) || !dev_alloc(c, &w.a, rows * h) || !dev_alloc(c, &w.qkv, rows * 3 * h) ||
         !dev_alloc(c, &w.g, rows * tw.ff) || !dev_alloc(c, &w.sel16, (size_t)items * h) || !dev_alloc(c, &w.sel32, (size_t)items * h) ||
         !dev_alloc(c, &w.proj32, (size_t)items * tw.proj)) return false;
     bool ok = make_tma_2d_16bit(&w.map_a, w.a, rows, h, h, GEMM_BN) && make_tma_2d_16bit(&w.map_g, w.g, rows, tw.ff, tw.ff, GEMM_BN) &&
@@ -243,7 +243,7 @@ bool ensure_ws(clip_ctx* c, Tower& tw, int items, int T, bool vision) {
               make_tma_2d_16bit(&w.map_q128, w.qkv, rows, 3 * h, 3 * h, 128) &&
               make_tma_2d_16bit(&w.map_kv16, w.qkv, rows, 3 * h, 3 * h, 16) &&
               make_tma_2d_16bit_plain(&w.map_out_qkv, w.qkv, rows, 3 * h, 3 * h, GEMM_OUT_BOX, GEMM_OUT_BOX) &&
-              make_tma_2d_16bit_plain(&w.map_out_d, w.d, rows, h, h, GEMM_OUT_BOX, GEMM_OUT_BOX) &&
+              make_tma_2d_f32_plain(&w.map_out_x32, w.x, rows, h, h, GEMM_OUT_BOX, GEMM_OUT_BOX) &&
               make_tma_2d_16bit_plain(&w.map_out_g, w.g, rows, tw.ff, tw.ff, GEMM_OUT_BOX, GEMM_OUT_BOX);
     if (vision) {
         const size_t per = (size_t)tw.image_size * tw.image_size * 3;
@@ -275,15 +275,16 @@ bool run_linear(clip_ctx* c, const Linear& L, const TmaMap* xmap, const void* xp
 
 // The per-layer schedule shared by both towers (clip.cpp:1064-1143 text, 1342-1423 vision).
 bool run_blocks(clip_ctx* c, Tower& tw, int nseq, int T, bool causal) {
-    // Residual adds are deferred: each branch GEMM (out-proj, FC2) stores its output 16-bit into w.d and the NEXT LayerNorm
-    // applies x += d while it reads x anyway.  On return one delta (the last FC2) is still pending in w.d.
+    // The residual stream x stays fp32 (as in the reference).  The branch GEMMs (out-proj, FC2) add their result INTO x themselves: the
+    // epilogue stages fp32 blocks in shared memory and a TMA tensor reduce-add (cp.reduce.async.bulk.tensor .add) performs x += acc + bias
+    // in the memory system -- the SMs never read x for it, and the traffic hides under the tensor-bound GEMM.  LayerNorm then only reads
+    // x and writes its 16-bit output: 6 B per element instead of the 12 B of the round-1 "deferred residual" scheme.
     Workspace& w = tw.ws;
     const int M = nseq * T, h = tw.hidden;
     const int bf = c->operand_bf16 ? 1 : 0;
     const float qscale = 1.0f / sqrtf(64.0f);
-    bool pending = false;
     for (auto& l : tw.L) {
-        { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln1_g, l.ln1_b, pending ? w.d : nullptr, w.a, bf, c->stream); }
+        { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln1_g, l.ln1_b, nullptr, w.a, bf, c->stream); }
         if (!run_linear(c, l.qkv, &w.map_a, w.a, bf, M, w.qkv, 3 * h, EPI_STORE16, bf, h, qscale, &w.map_a_half, &w.map_out_qkv)) return false;
         if (c->attn_tc && attention_tc_supported(T)) {
             const int q_done = attention_tc_tiles(T) * 128;
@@ -292,11 +293,10 @@ bool run_blocks(clip_ctx* c, Tower& tw, int nseq, int T, bool causal) {
         } else {
             Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, 0, c->stream);
         }
-        if (!run_linear(c, l.out, &w.map_a, w.a, bf, M, w.d, h, EPI_STORE16, bf, 0, 1.f, &w.map_a_half, &w.map_out_d)) return false;
-        { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln2_g, l.ln2_b, w.d, w.a, bf, c->stream); }
+        if (!run_linear(c, l.out, &w.map_a, w.a, bf, M, w.x, h, EPI_REDADD32, 0, 0, 1.f, &w.map_a_half, &w.map_out_x32)) return false;
+        { Scope s(c, K_LN); launch_layernorm(w.x, h, M, h, tw.eps, l.ln2_g, l.ln2_b, nullptr, w.a, bf, c->stream); }
         if (!run_linear(c, l.fc1, &w.map_a, w.a, bf, M, w.g, tw.ff, c->use_gelu ? EPI_GELU16 : EPI_QGELU16, bf, 0, 1.f, &w.map_a_half, &w.map_out_g)) return false;
-        if (!run_linear(c, l.fc2, &w.map_g, w.g, bf, M, w.d, h, EPI_STORE16, bf, 0, 1.f, &w.map_g_half, &w.map_out_d)) return false;
-        pending = true;
+        if (!run_linear(c, l.fc2, &w.map_g, w.g, bf, M, w.x, h, EPI_REDADD32, 0, 0, 1.f, &w.map_g_half, &w.map_out_x32)) return false;
     }
     CK(cudaGetLastError());
     return true;
@@ -313,7 +313,7 @@ bool vision_forward(clip_ctx* c, const float* d_pixels, int nb, float* d_out, bo
     { Scope s(c, K_OTHER); launch_assemble_preln(w.patch32, tw.class_embd, tw.pos, nb, tw.T, h, tw.eps, tw.pre_g, tw.pre_b, w.x, c->stream); }
     if (!run_blocks(c, tw, nb, tw.T, false)) return false;
     // CLS rows -> post-LN -> projection -> (L2 norm)   (clip.cpp:1426-1455)
-    { Scope s(c, K_LN); launch_layernorm(w.x, (size_t)tw.T * h, nb, h, tw.eps, tw.post_g, tw.post_b, tw.layers ? w.d : nullptr, w.sel16, bf, c->stream); }
+    { Scope s(c, K_LN); launch_layernorm(w.x, (size_t)tw.T * h, nb, h, tw.eps, tw.post_g, tw.post_b, nullptr, w.sel16, bf, c->stream); }
     if (!run_linear(c, tw.proj_w, &w.map_sel, w.sel16, bf, nb, w.proj32, tw.proj, EPI_STORE32, 0)) return false;
     { Scope s(c, K_OTHER); launch_l2norm(w.proj32, d_out, nb, tw.proj, normalize ? 1 : 0, c->stream); }
     CK(cudaGetLastError());
@@ -328,7 +328,7 @@ bool text_forward(clip_ctx* c, int nb, int T, float* d_out, bool normalize) {
     { Scope s(c, K_OTHER); launch_text_embed(w.ids, tw.tok, tw.pos, nb, T, h, tw.n_vocab, w.x, c->stream); }
     if (!run_blocks(c, tw, nb, T, true)) return false;
     // final LN is row-wise, so LN(select(EOT)) == select(LN(all)) (clip.cpp:1146-1155)
-    { Scope s(c, K_OTHER); launch_gather_rows(w.x, w.sel32, nb, h, T, w.last, tw.layers ? w.d : nullptr, bf, c->stream); }
+    { Scope s(c, K_OTHER); launch_gather_rows(w.x, w.sel32, nb, h, T, w.last, nullptr, bf, c->stream); }
     { Scope s(c, K_LN); launch_layernorm(w.sel32, h, nb, h, tw.eps, tw.post_g, tw.post_b, nullptr, w.sel16, bf, c->stream); }
     if (!run_linear(c, tw.proj_w, &w.map_sel, w.sel16, bf, nb, w.proj32, tw.proj, EPI_STORE32, 0)) return false;
     { Scope s(c, K_OTHER); launch_l2norm(w.proj32, d_out, nb, tw.proj, normalize ? 1 : 0, c->stream); }
@@ -368,6 +368,19 @@ int default_micro_batch(int T) {   // 37 token tiles = 148/4: every N/128 that i
 void chunking(size_t n, int mb, size_t& n_chunks, size_t& chunk) {
     n_chunks = (n + mb - 1) / mb;
     chunk = (n + n_chunks - 1) / n_chunks;
+}
+
+// Chunk boundaries for inputs that still have to cross PCIe: the host->device copy of the FIRST micro-batch cannot hide under any
+// kernel, so it is made small (a quarter of a micro-batch); the rest is split into balanced micro-batches as usual.
+std::vector<size_t> host_chunk_bounds(size_t n, int mb) {
+    std::vector<size_t> b{0};
+    if (n <= (size_t)mb) { b.push_back(n); return b; }
+    const size_t head = std::max<size_t>(1, (size_t)mb / 4);
+    b.push_back(head);
+    size_t n_chunks, chunk;
+    chunking(n - head, mb, n_chunks, chunk);
+    for (size_t i0 = head; i0 < n; i0 += chunk) b.push_back(std::min(n, i0 + chunk));
+    return b;
 }
 
 bool sync_and_time(clip_ctx* c) {
@@ -772,8 +785,7 @@ static bool image_batch_encode_one(clip_ctx* c, int n_threads, const clip_image_
     CK(cudaSetDevice(c->device));
     if (!ensure_ws(c, tw, tw.micro_batch, tw.T, true)) return false;
     if (!d_vec) { if (!ensure_out(c, n * tw.proj)) return false; d_vec = c->d_out; }
-    size_t n_chunks, chunk;
-    chunking(n, tw.micro_batch, n_chunks, chunk);
+    const std::vector<size_t> bounds = host_chunk_bounds(n, tw.micro_batch);
     const size_t per = (size_t)tw.image_size * tw.image_size * 3;
     bool pinned = true;
     for (size_t i = 0; i < n && pinned; i++) pinned = host_ptr_is_pinned(imgs[i].data);
@@ -786,9 +798,9 @@ static bool image_batch_encode_one(clip_ctx* c, int n_threads, const clip_image_
     }
     const int nt = std::max(1, std::min({std::max(n_threads, 4), 16, (int)std::thread::hardware_concurrency()}));
     CK(cudaEventRecord(c->ev_t0, c->stream));
-    size_t ci = 0;
-    for (size_t i0 = 0; i0 < n; i0 += chunk, ci++) {
-        const int nb = (int)std::min(chunk, n - i0), b = (int)(ci & 1);
+    for (size_t ci = 0; ci + 1 < bounds.size(); ci++) {
+        const size_t i0 = bounds[ci];
+        const int nb = (int)(bounds[ci + 1] - i0), b = (int)(ci & 1);
         if (ci >= 2) CK(cudaStreamWaitEvent(c->copy_stream, c->ev_consumed[b], 0));
         if (pinned) {
             for (int j = 0; j < nb; j++)
@@ -1394,12 +1406,11 @@ int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int e
                          const float* bias, const float* resid_in, float* y_out, float* ms) {
     g_err.clear();
     if (gemm_init() != cudaSuccess) { set_err("gemm_init failed"); return 1; }
-    (void)resid_in;      // kept in the signature for ABI stability: the read-modify-write epilogue it fed is gone
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, dev);
-    const bool out32 = (epi == EPI_STORE32);
+    const bool out32 = (epi == EPI_STORE32 || epi == EPI_REDADD32);
     int eff_q = qtype;
     std::vector<uint16_t> x16((size_t)M * K);
     for (size_t i = 0; i < x16.size(); i++) x16[i] = operand_bf16 ? f32_to_bf16(x[i]) : f32_to_f16(x[i]);
@@ -1435,11 +1446,13 @@ int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int e
         if (eff_q == QT_F16) d_w = d_raw;
         else { if ((e = cudaMalloc(&d_w, wdev.size())) != cudaSuccess) { fail("malloc w", e); break; } cudaMemcpy(d_w, wdev.data(), wdev.size(), cudaMemcpyHostToDevice); }
         if (bias) { cudaMalloc(&d_bias, (size_t)N * 4); cudaMemcpy(d_bias, bias, (size_t)N * 4, cudaMemcpyHostToDevice); }
-        cudaMemset(d_out, 0, out_bytes);
+        if (epi == EPI_REDADD32 && resid_in) cudaMemcpy(d_out, resid_in, out_bytes, cudaMemcpyHostToDevice);
+        else cudaMemset(d_out, 0, out_bytes);
         TmaMap xm, xh, wm, om;
         memset(&wm, 0, sizeof(wm));
-        const bool use_out_map = !out32 && !(getenv("CLIP_B200_DEBUG_DIRECT_STORE") && atoi(getenv("CLIP_B200_DEBUG_DIRECT_STORE")) != 0);
-        if (use_out_map && !make_tma_2d_16bit_plain(&om, d_out, M, N, N, GEMM_OUT_BOX, GEMM_OUT_BOX)) { set_err("tensor map OUT failed"); rc = 4; break; }
+        const bool use_out_map = epi != EPI_STORE32 && !(getenv("CLIP_B200_DEBUG_DIRECT_STORE") && atoi(getenv("CLIP_B200_DEBUG_DIRECT_STORE")) != 0);
+        if (use_out_map && !(out32 ? make_tma_2d_f32_plain(&om, d_out, M, N, N, GEMM_OUT_BOX, GEMM_OUT_BOX)
+                                   : make_tma_2d_16bit_plain(&om, d_out, M, N, N, GEMM_OUT_BOX, GEMM_OUT_BOX))) { set_err("tensor map OUT failed"); rc = 4; break; }
         if (!make_tma_2d_16bit(&xm, d_x, M, K, K, GEMM_BN) || !make_tma_2d_16bit(&xh, d_x, M, K, K, GEMM_BN / 2)) { set_err("tensor map X failed"); rc = 4; break; }
         if (eff_q == QT_F16 && !make_tma_2d_16bit(&wm, d_w, N, K, K, GEMM_BM)) { set_err("tensor map W failed"); rc = 4; break; }
         cudaEventRecord(e0, st);

@@ -24,7 +24,7 @@ enum Epi : int {
     EPI_STORE16 = 0,      // out16 = (acc + bias) [* scale for the first scale_cols features]
     EPI_GELU16 = 1,       // out16 = gelu_tanh(acc + bias)          (clip.use_gelu = true)
     EPI_QGELU16 = 2,      // out16 = quick_gelu(acc + bias)         (clip.use_gelu = false)
-    /* 3 was a read-modify-write residual epilogue: latency-bound, replaced by the deferred add in LayerNorm */
+    EPI_REDADD32 = 3,     // x32 += acc + bias  (fp32 residual stream): staged in shared memory, added by a TMA tensor REDUCE
     EPI_STORE32 = 4,      // out32 = acc + bias
 };
 
@@ -154,6 +154,14 @@ CB_DEVINL void tma_store_2d(const void* tmap, uint32_t src_smem, int c0, int c1)
                  "r"(c0), "r"(c1)
                  : "memory");
 }
+// TMA tensor REDUCE (shared -> global, element-wise add performed by the memory system): out[box] += smem[box].  Each output element is
+// owned by exactly one CTA, so the result is deterministic.
+CB_DEVINL void tma_reduce_add_2d(const void* tmap, uint32_t src_smem, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+                 "r"(src_smem), "r"(c0), "r"(c1)
+                 : "memory");
+}
+CB_DEVINL void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 CB_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 CB_DEVINL void bulk_wait_group_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }

@@ -19,6 +19,9 @@ bool make_tma_2d_16bit(TmaMap* out, const void* gptr, uint64_t rows, uint64_t co
 // (box 32 tokens x 32 features = 32 rows of 64 bytes).
 bool make_tma_2d_16bit_plain(TmaMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
                              uint32_t box_cols);
+// the same over an fp32 matrix: target of the EPI_REDADD32 epilogue's TMA reduce-add (the residual stream)
+bool make_tma_2d_f32_plain(TmaMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                           uint32_t box_cols);
 constexpr int GEMM_OUT_BOX = 32;
 
 constexpr int GEMM_BM = 128;   // features per tile (UMMA M / TMEM lanes)
@@ -35,7 +38,8 @@ struct GemmArgs {
     bool operand_bf16 = false;       // X (and the unpacked W) are bf16 instead of fp16; must be false for QT_F16
     const float* bias = nullptr;     // [N] or null
     void* out = nullptr;             // EPI_*16: 16-bit [M, ldo]; EPI_*32: fp32 [M, ldo]
-    const TmaMap* out_map = nullptr; // optional, 16-bit epilogues of quantized GEMMs: plain map of `out` (box GEMM_OUT_BOX x GEMM_OUT_BOX): the
+    const TmaMap* out_map = nullptr; // 16-bit epilogues (optional) and EPI_REDADD32 (required unless the direct path is wanted) of quantized
+                                     // GEMMs: plain map of `out` (16-bit, resp. fp32; box GEMM_OUT_BOX x GEMM_OUT_BOX): the
                                      // epilogue stages 32 x 32 blocks in shared memory and stores them with TMA instead of 2-byte STGs.
                                      // NOTE rows of the last token tile beyond M are written too when the map has more than M rows.
     int M = 0, N = 0, K = 0, ldo = 0;

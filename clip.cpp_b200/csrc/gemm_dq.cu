@@ -62,8 +62,8 @@ struct Cfg {
     static constexpr int SQ = DQ ? 8 : 0;                              // packed-weight ring
     static constexpr uint32_t XS = DQ ? (uint32_t)(PAIR ? X_STAGE / 2 : X_STAGE) : (uint32_t)(X_STAGE + W_STAGE);
     static constexpr uint32_t Q_OFF = SX * XS;
-    static constexpr uint32_t OUT_OFF = Q_OFF + SQ * CHUNK;            // epilogue staging: 4 warps x 2 buffers x [32 tokens x 32 features] 16-bit
-    static constexpr uint32_t OUT_BYTES = DQ ? 4 * 2 * 2048 : 0;
+    static constexpr uint32_t OUT_OFF = Q_OFF + SQ * CHUNK;            // epilogue staging: 4 warps x 2 buffers x [32 tokens x 32 features] (16-bit or fp32)
+    static constexpr uint32_t OUT_BYTES = DQ ? 4 * 2 * 4096 : 0;
     static constexpr uint32_t BAR_OFF = (OUT_OFF + OUT_BYTES + 127) / 128 * 128;
     static constexpr uint32_t SMEM = BAR_OFF + 512 /*barriers*/ + 1024 /*align slack*/;
     static_assert(SMEM <= 232448, "shared memory plan exceeds 227 KB");
@@ -225,6 +225,12 @@ CB_DEVINL void epilogue_chunk(const KParams& p, const uint32_t (&r)[32], uint32_
         #pragma unroll
         for (int j = 0; j < 32; j++, o += ldo)
             if (FULL || j < nvalid) base[o] = __uint_as_float(r[j]) + bias;
+    } else if constexpr (EPI == EPI_REDADD32) {      // direct fallback (no output map): every element belongs to exactly one thread
+        float* base = reinterpret_cast<float*>(p.out);
+        uint32_t o = off;
+        #pragma unroll
+        for (int j = 0; j < 32; j++, o += ldo)
+            if (FULL || j < nvalid) base[o] += __uint_as_float(r[j]) + bias;
     } else {
         uint16_t* base = reinterpret_cast<uint16_t*>(p.out);
         uint32_t o = off;
@@ -246,19 +252,26 @@ CB_DEVINL void epilogue_tile_tma(const KParams& p, uint32_t acc_addr, int tok0, 
     #pragma unroll 1
     for (int c = 0; c < BN / 32; c++) {
         if (ntok - c * 32 <= 0) break;             // warp-uniform
-        const uint32_t buf = stage + (cidx & 1u) * 2048u;
+        const uint32_t buf = stage + (cidx & 1u) * 4096u;
         cidx++;
         if (lane == 0) bulk_wait_group_read<1>();  // the store that last used THIS buffer (two chunks ago) has read it
         __syncwarp();
         uint32_t r[32];
         tmem_ld_32x32(acc_addr + c * 32, r);
         tmem_ld_wait();
-        #pragma unroll
-        for (int j = 0; j < 32; j++) sts16(buf + (uint32_t)j * 64u + (uint32_t)lane * 2u, P2<BF>::from_float(epi_value<EPI>(__uint_as_float(r[j]), bias, mul)));
+        if constexpr (EPI == EPI_REDADD32) {
+            // fp32 residual stream: x[tok, n] += acc + bias.  Row = token (128 B: one conflict-free wavefront), then ONE TMA reduce-add.
+            #pragma unroll
+            for (int j = 0; j < 32; j++) sts32(buf + (uint32_t)j * 128u + (uint32_t)lane * 4u, __float_as_uint(__uint_as_float(r[j]) + bias));
+        } else {
+            #pragma unroll
+            for (int j = 0; j < 32; j++) sts16(buf + (uint32_t)j * 64u + (uint32_t)lane * 2u, P2<BF>::from_float(epi_value<EPI>(__uint_as_float(r[j]), bias, mul)));
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-            tma_store_2d(&p.tm_out, buf, n0, tok0 + c * 32);
+            if constexpr (EPI == EPI_REDADD32) tma_reduce_add_2d(&p.tm_out, buf, n0, tok0 + c * 32);
+            else tma_store_2d(&p.tm_out, buf, n0, tok0 + c * 32);
             bulk_commit_group();
         }
     }
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         int it = 0;
         uint32_t cidx = 0;
-        const uint32_t out_stage = smem_base + C::OUT_OFF + (uint32_t)(warp & 3) * 4096u;
+        const uint32_t out_stage = smem_base + C::OUT_OFF + (uint32_t)(warp & 3) * 8192u;
         const bool tma_out = DQ && p.tma_out && !(CB_DBG(p, 24));
         for (int tile = first; tile < n_tiles; tile += stride, it++) {
             const int ft = PAIR ? (tile % n_ft) * 2 + (int)rank : tile % n_ft, tt = tile / n_ft;
@@ -492,6 +505,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
                 switch (p.epi) {
                 case EPI_GELU16: epilogue_tile_tma<EPI_GELU16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                 case EPI_QGELU16: epilogue_tile_tma<EPI_QGELU16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
+                case EPI_REDADD32: epilogue_tile_tma<EPI_REDADD32, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                 default: epilogue_tile_tma<EPI_STORE16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                 }
             } else
@@ -499,6 +513,7 @@ __global__ void __launch_bounds__(QT == QT_F16 ? 256 : 512, 1) gemm_dq_kernel(co
             case EPI_STORE16: epilogue_tile<EPI_STORE16, BF>(p, acc_addr, tok0, n, bias, mul); break;
             case EPI_GELU16: epilogue_tile<EPI_GELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
             case EPI_QGELU16: epilogue_tile<EPI_QGELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
+            case EPI_REDADD32: epilogue_tile<EPI_REDADD32, BF>(p, acc_addr, tok0, n, bias, mul); break;
             default: epilogue_tile<EPI_STORE32, BF>(p, acc_addr, tok0, n, bias, mul); break;
             }
             tc_fence_before();
@@ -690,7 +705,7 @@ __global__ void __launch_bounds__(512, 1) gemm_dq2_kernel(const __grid_constant_
         const int fr = (warp & 3) * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t cidx = 0, u0 = 0, u1 = 0;
-        const uint32_t out_stage = smem_base + C::OUT_OFF + (uint32_t)(warp & 3) * 4096u;
+        const uint32_t out_stage = smem_base + C::OUT_OFF + (uint32_t)(warp & 3) * 8192u;
         const bool tma_out = p.tma_out && !(CB_DBG(p, 24));
         for (int g = first; get_work(g, n_ft, n_super, full, p.M, w); g += stride) {
             if (w.nh == 0) continue;
@@ -708,12 +723,14 @@ __global__ void __launch_bounds__(512, 1) gemm_dq2_kernel(const __grid_constant_
                     switch (p.epi) {
                     case EPI_GELU16: epilogue_tile_tma<EPI_GELU16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                     case EPI_QGELU16: epilogue_tile_tma<EPI_QGELU16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
+                    case EPI_REDADD32: epilogue_tile_tma<EPI_REDADD32, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                     default: epilogue_tile_tma<EPI_STORE16, BF>(p, acc_addr, tok0, n0, bias, mul, out_stage, cidx, lane); break;
                     }
                 } else if (!(CB_DBG(p, 8))) switch (p.epi) {
                 case EPI_STORE16: epilogue_tile<EPI_STORE16, BF>(p, acc_addr, tok0, n, bias, mul); break;
                 case EPI_GELU16: epilogue_tile<EPI_GELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
                 case EPI_QGELU16: epilogue_tile<EPI_QGELU16, BF>(p, acc_addr, tok0, n, bias, mul); break;
+                case EPI_REDADD32: epilogue_tile<EPI_REDADD32, BF>(p, acc_addr, tok0, n, bias, mul); break;
                 default: epilogue_tile<EPI_STORE32, BF>(p, acc_addr, tok0, n, bias, mul); break;
                 }
                 tc_fence_before();
@@ -833,6 +850,19 @@ bool make_tma_2d_16bit_plain(TmaMap* out, const void* gptr, uint64_t rows, uint6
     return r == CUDA_SUCCESS;
 }
 
+bool make_tma_2d_f32_plain(TmaMap* out, const void* gptr, uint64_t rows, uint64_t cols, uint64_t row_stride_elems, uint32_t box_rows,
+                           uint32_t box_cols) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {row_stride_elems * 4};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 cudaError_t gemm_init() {
     cudaError_t e;
     if ((e = set_attr<QT_F16, false>()) != cudaSuccess) return e;
@@ -859,7 +889,7 @@ cudaError_t gemm_launch(const GemmArgs& a, cudaStream_t stream, int num_sms, uin
     else memset(&kp.tm_xh, 0, sizeof(CUtensorMap));
     const bool epi16 = (a.epi == EPI_STORE16 || a.epi == EPI_GELU16 || a.epi == EPI_QGELU16);
     static const bool tma_store_off = getenv("CLIP_B200_GEMM_TMA_STORE") && atoi(getenv("CLIP_B200_GEMM_TMA_STORE")) == 0;
-    kp.tma_out = (a.out_map && epi16 && a.qtype != QT_F16 && !tma_store_off) ? 1 : 0;
+    kp.tma_out = (a.out_map && (epi16 || a.epi == EPI_REDADD32) && a.qtype != QT_F16 && !tma_store_off) ? 1 : 0;
     if (kp.tma_out) memcpy(&kp.tm_out, a.out_map, sizeof(CUtensorMap));
     else memset(&kp.tm_out, 0, sizeof(CUtensorMap));
     kp.w_packed = a.w_packed;

@@ -222,7 +222,8 @@ __global__ void naive_gemm_kernel(const uint16_t* __restrict__ x, int x_bf16, co
     }
     float v = acc + (bias ? bias[n] : 0.f);
     const size_t o = (size_t)m * ldo + n;
-    if (epi == EPI_STORE32) reinterpret_cast<float*>(out)[o] = v;
+    if (epi == EPI_REDADD32) reinterpret_cast<float*>(out)[o] += v;
+    else if (epi == EPI_STORE32) reinterpret_cast<float*>(out)[o] = v;
     else {
         if (epi == EPI_GELU16) v = gelu_tanh(v);
         else if (epi == EPI_QGELU16) v = gelu_quick(v);

@@ -32,7 +32,6 @@ struct Workspace {
     int cap_items = 0, T = 0, cap_rows = 0;
     float* x = nullptr;          // residual stream fp32 [rows, h]
     uint16_t* a = nullptr;       // LN output / attention output 16-bit [rows, h]
-    uint16_t* d = nullptr;       // pending residual branch (out-proj / FC2 output) 16-bit [rows, h]
     uint16_t* qkv = nullptr;     // [rows, 3h]
     uint16_t* g = nullptr;       // [rows, ff]
     uint16_t* sel16 = nullptr;   // CLS / EOT rows after post-LN [items, h]
@@ -48,7 +47,8 @@ struct Workspace {
     TmaMap map_a, map_g, map_patches, map_sel;
     TmaMap map_a_half, map_g_half;          // box of GEMM_BN/2 tokens: B-operand halves of the CTA-pair GEMM
     TmaMap map_q128, map_kv16;              // views of qkv for the tcgen05 attention kernel (K / V: per-launch 3-D view)
-    TmaMap map_out_qkv, map_out_d, map_out_g;   // plain 32 x 32 boxes: TMA-store targets of the GEMM epilogue
+    TmaMap map_out_qkv, map_out_g;          // plain 32 x 32 boxes: TMA-store targets of the GEMM epilogue (16-bit)
+    TmaMap map_out_x32;                     // fp32 view of the residual stream x: TMA reduce-add target of the out-proj / FC2 epilogue
 };
 
 struct Tower {

@@ -11,7 +11,7 @@ import oracle as orc
 pytestmark = pytest.mark.gpu
 
 QT = {"f16": 1, "q4_0": 2, "q4_1": 3, "q5_0": 6, "q5_1": 7, "q8_0": 8}
-EPI_STORE16, EPI_GELU16, EPI_QGELU16, _EPI_RETIRED, EPI_STORE32 = range(5)
+EPI_STORE16, EPI_GELU16, EPI_QGELU16, EPI_REDADD32, EPI_STORE32 = range(5)
 
 
 def round16(a, bf16):
@@ -101,6 +101,8 @@ def expected(x, deq, bias, bf16, epi, resid, N):
     v = acc + (bias if bias is not None else 0)
     if epi == EPI_STORE32:
         return v
+    if epi == EPI_REDADD32:
+        return resid + v
     if epi == EPI_GELU16:
         v = 0.5 * v * (1 + np.tanh(0.7978845608 * v * (1 + 0.044715 * v * v)))
     elif epi == EPI_QGELU16:
@@ -127,7 +129,7 @@ def test_gemm_all_types_store32(prod, qt, bf16):
     assert err <= 2e-3 * max(1.0, np.abs(ref).max()), (qt, bf16, err)
 
 
-@pytest.mark.parametrize("epi", [EPI_STORE16, EPI_GELU16, EPI_QGELU16, EPI_STORE32])
+@pytest.mark.parametrize("epi", [EPI_STORE16, EPI_GELU16, EPI_QGELU16, EPI_REDADD32, EPI_STORE32])
 @pytest.mark.parametrize("bf16", [True, False])
 def test_gemm_epilogues(prod, epi, bf16):
     rng = np.random.default_rng(2)
@@ -177,7 +179,7 @@ def test_gemm_large_persistent(prod):
     print("gemm %dx%dx%d q4_0: %.3f ms  %.1f TFLOP/s" % (M, N, K, ms, 2.0 * M * N * K / ms / 1e9))
 
 
-@pytest.mark.parametrize("epi", [EPI_STORE16, EPI_QGELU16])
+@pytest.mark.parametrize("epi", [EPI_STORE16, EPI_QGELU16, EPI_REDADD32])
 def test_gemm_direct_store_epilogue_still_matches(prod, epi, monkeypatch):
     """16-bit epilogues normally leave through shared memory + TMA store; the direct 2-byte store path (no output tensor map, e.g.
     an output buffer the caller did not describe) must give the same bits."""
@@ -186,9 +188,10 @@ def test_gemm_direct_store_epilogue_still_matches(prod, epi, monkeypatch):
     raw, deq = make_weight("q4_0", N, K, rng)
     x = rng.standard_normal((M, K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
-    a, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias)
+    resid = rng.standard_normal((M, N)).astype(np.float32)
+    a, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias, resid)
     monkeypatch.setenv("CLIP_B200_DEBUG_DIRECT_STORE", "1")
-    b, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias)
+    b, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias, resid)
     assert np.array_equal(a, b)
 
 
@@ -208,7 +211,7 @@ def test_gemm_wide_form_all_types(prod, qt, bf16, monkeypatch):
 
 
 @pytest.mark.parametrize("M", [74 * 384, 74 * 384 + 1, 75 * 384 - 191, 75 * 384 + 193, 111 * 384 + 7])
-@pytest.mark.parametrize("epi", [EPI_STORE16, EPI_QGELU16])
+@pytest.mark.parametrize("epi", [EPI_STORE16, EPI_QGELU16, EPI_REDADD32])
 def test_gemm_wide_form_tails_and_epilogues(prod, M, epi, monkeypatch):
     """wide kernel: exact multiples, one extra row, a lone first half, a ragged second half, 1.5 waves; 16-bit epilogues via TMA store"""
     monkeypatch.setenv("CLIP_B200_GEMM_WIDE", "1")
@@ -217,6 +220,7 @@ def test_gemm_wide_form_tails_and_epilogues(prod, M, epi, monkeypatch):
     raw, deq = make_weight("q4_0", N, K, rng)
     x = rng.standard_normal((M, K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
-    y, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias)
-    ref = expected(x, deq, bias, True, epi, None, N)
+    resid = rng.standard_normal((M, N)).astype(np.float32)
+    y, _ = run_gemm(prod, "q4_0", True, M, N, K, epi, x, raw, bias, resid)
+    ref = expected(x, deq, bias, True, epi, resid, N)
     assert np.abs(y - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max())
