@@ -51,7 +51,7 @@ static_assert(KV_BYTES % 1024 == 0 && Q_OFF % 1024 == 0, "tile alignment");
 struct AParams {
     CUtensorMap tm_q, tm_kv256, tm_kv16;
     uint16_t* out;
-    int T, H, nseq, causal, ntile, nk16, last_row;
+    int T, H, nseq, causal, ntile, nk16, last_row, desc;
 };
 
 CB_DEVINL void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         // (sequence, head), then its 128-query tiles
         int g = 0;
         for (int i = 0; i < n_local; i++) {
-            const int item = blockIdx.x + i * gridDim.x, head = item % p.H, seq = item / p.H;
+            const int item = p.desc ? nitems - 1 - ((int)blockIdx.x + i * (int)gridDim.x) : (int)blockIdx.x + i * (int)gridDim.x, head = item % p.H, seq = item / p.H;   // descending: the QKV GEMM's last rows are in L2
             const uint32_t st = i & 1, k_s = smem_base + st * (2 * KV_BYTES), v_s = k_s + KV_BYTES;
             const int row0 = seq * p.T, c = head * DH;
             mbar_wait(kv_empty + 8 * st, ((i >> 1) & 1) ^ 1);
@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
             const uint32_t k_s = smem_base + st * (2 * KV_BYTES), v_s = k_s + KV_BYTES, qx = smem_base + QX_OFF + st * 2048;
             int j = 0;
             for (int i = st; i < n_local; i += 2, j++) {
-                const int item = blockIdx.x + i * gridDim.x, head = item % p.H, seq = item / p.H;
+                const int item = p.desc ? nitems - 1 - ((int)blockIdx.x + i * (int)gridDim.x) : (int)blockIdx.x + i * (int)gridDim.x, head = item % p.H, seq = item / p.H;   // descending: the QKV GEMM's last rows are in L2
                 mbar_wait(kv_full + 8 * st, j & 1);
                 mbar_wait(qx_full + 8 * st, j & 1);
                 uint32_t qp[32];                            // the query row, packed 16-bit pairs (unpacked on the fly: registers are scarce)
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
         for (int g = grp; g < G; g += 2) {
             const uint32_t jp = (g >> 1) & 1;
             const int i = g / ntile, qt = g - i * ntile;
-            const int item = blockIdx.x + i * gridDim.x, head = item % p.H, seq = item / p.H;
+            const int item = p.desc ? nitems - 1 - ((int)blockIdx.x + i * (int)gridDim.x) : (int)blockIdx.x + i * (int)gridDim.x, head = item % p.H, seq = item / p.H;   // descending: the QKV GEMM's last rows are in L2
             const uint32_t k_s = smem_base + (i & 1) * (2 * KV_BYTES), v_s = k_s + KV_BYTES;
             const int qrow = qt * AQ + r;
             const int klim = p.causal ? min(p.T, qrow + 1) : p.T;      // keys [0, klim) are visible to this row
@@ -509,6 +509,8 @@ cudaError_t launch_attention_tc(const TmaMap* map_q, const void* qkv16, const Tm
     p.last_row = (T > 1 && T % AQ == 1) ? 1 : 0;      // e.g. 257 = 2 tensor-core tiles + one row on the CUDA cores
     p.ntile = (T - p.last_row + AQ - 1) / AQ;
     p.nk16 = ((T + 15) / 16) * 16;
+    static const int desc = (getenv("CLIP_B200_ORDER") && !strcmp(getenv("CLIP_B200_ORDER"), "attn_desc")) ? 1 : 0;      // A/B switch for measurements
+    p.desc = desc;
     const int total = nseq * H;
     const int grid = total < num_sms ? total : num_sms;      // one persistent CTA per SM, items = (sequence, head)
     cudaError_t e = bf16 ? launch_pdl(attention_tc_kernel<true>, (unsigned)grid, (unsigned)ATT_THREADS, ATT_SMEM, st, 1, p)

@@ -1,6 +1,9 @@
 // kernels.cu -- the memory-bound kernels around the GEMMs: LayerNorm (K2), im2col (K0a), embedding assembly (K4),
 // L2-normalise (K5), zero-shot scoring, plus a scalar debug GEMM.  All are HBM-bound streaming kernels: one warp per
 // row, 128-bit coalesced loads, warp-shuffle reductions, no shared memory.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -14,6 +17,16 @@ CB_DEVINL float warp_sum(float v) {
     return v;
 }
 CB_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// L2 residency hints for the LayerNorm streams: x is read ONCE here and next touched by a reduce-add a whole GEMM later (evict first);
+// the 16-bit output is the very next GEMM's operand (keep it: 135 MB of output vs 126 MB of L2)
+CB_DEVINL float4 ld4_evict_first(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L2::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+CB_DEVINL void st2_evict_last(uint16_t* p, uint2 v) {
+    asm volatile("st.global.L2::evict_last.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
 CB_DEVINL float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // Two-pass LayerNorm statistics over a row produced by `load(i4)` (i4 = float4 index), as the reference does:
@@ -41,11 +54,14 @@ CB_DEVINL void row_stats(Load load, int h4, int lane, float inv_h, float eps, fl
 template <bool BF, bool DELTA, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, size_t in_stride, int rows, int h, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        const uint16_t* __restrict__ delta, uint16_t* __restrict__ y) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+                                                        const uint16_t* __restrict__ delta, uint16_t* __restrict__ y, int descending) {
+    // rows are walked from the LAST to the first: the GEMM before this kernel produced x in ascending token order, so its last rows are
+    // the ones still in the 126 MB L2, and the GEMM after it starts with token tile 0, i.e. with the rows written here last
+    const int lin = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int row = descending ? rows - 1 - lin : lin;
     pdl_trigger();
     pdl_wait();
-    if (row >= rows) return;
+    if (lin >= rows) return;
     float* xr = x + (size_t)row * in_stride;
     const uint16_t* dr = DELTA ? delta + (size_t)row * in_stride : nullptr;
     const int h4 = h >> 2;
@@ -55,7 +71,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, s
     for (int j = 0; j < MAXV; j++) {
         const int i = lane + 32 * j;
         if (i < h4) {
-            v[j] = ld4(xr + 4 * i);
+            if constexpr (DELTA) v[j] = ld4(xr + 4 * i); else v[j] = ld4_evict_first(xr + 4 * i);
             if constexpr (DELTA) {
                 const uint2 d = *reinterpret_cast<const uint2*>(dr + 4 * i);
                 v[j].x += P2<BF>::to_float((uint16_t)(d.x & 0xffffu)); v[j].y += P2<BF>::to_float((uint16_t)(d.x >> 16));
@@ -86,7 +102,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, s
             uint2 pk;
             pk.x = (uint32_t)P2<BF>::from_float(o0) | ((uint32_t)P2<BF>::from_float(o1) << 16);
             pk.y = (uint32_t)P2<BF>::from_float(o2) | ((uint32_t)P2<BF>::from_float(o3) << 16);
-            *reinterpret_cast<uint2*>(yr + 4 * i) = pk;
+            st2_evict_last(yr + 4 * i, pk);
         }
     }
 }
@@ -242,7 +258,8 @@ void launch_layernorm(float* x, size_t in_stride, int rows, int h, float eps, co
     const int grid = rows_grid(rows, 8);
     const uint16_t* d = (const uint16_t*)delta16;
     uint16_t* y = (uint16_t*)y16;
-#define CB_LN(BFV, DV, MV) (void)launch_pdl(layernorm_kernel<BFV, DV, MV>, (unsigned)grid, 256u, 0, st, 1, x, in_stride, rows, h, eps, gamma, beta, d, y)
+    static const int desc = !(getenv("CLIP_B200_ORDER") && !strcmp(getenv("CLIP_B200_ORDER"), "asc"));      // A/B switch for measurements
+#define CB_LN(BFV, DV, MV) (void)launch_pdl(layernorm_kernel<BFV, DV, MV>, (unsigned)grid, 256u, 0, st, 1, x, in_stride, rows, h, eps, gamma, beta, d, y, desc)
 #define CB_LN_W(BFV, DV) do { if (h <= 512) CB_LN(BFV, DV, 4); else if (h <= 1024) CB_LN(BFV, DV, 8); else CB_LN(BFV, DV, 16); } while (0)
     if (bf16) { if (d) CB_LN_W(true, true); else CB_LN_W(true, false); }
     else      { if (d) CB_LN_W(false, true); else CB_LN_W(false, false); }
