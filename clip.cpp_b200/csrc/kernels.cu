@@ -17,19 +17,6 @@ CB_DEVINL float warp_sum(float v) {
     return v;
 }
 CB_DEVINL float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-// L2 residency hints for the LayerNorm streams: x is read ONCE here and next touched by a reduce-add a whole GEMM later (evict first);
-// the 16-bit output is the very next GEMM's operand (keep it: 135 MB of output vs 126 MB of L2)
-CB_DEVINL uint64_t l2_policy_evict_first() { uint64_t p; asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
-CB_DEVINL uint64_t l2_policy_evict_last() { uint64_t p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
-CB_DEVINL float4 ld4_hint(const float* p, uint64_t pol) {
-    float4 v;
-    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-CB_DEVINL void st2_hint(uint16_t* p, uint2 v, uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
-}
-
 CB_DEVINL float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // Two-pass LayerNorm statistics over a row produced by `load(i4)` (i4 = float4 index), as the reference does:
@@ -62,7 +49,6 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, s
     // the ones still in the 126 MB L2, and the GEMM after it starts with token tile 0, i.e. with the rows written here last
     const int lin = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int row = descending ? rows - 1 - lin : lin;
-    const uint64_t pol_in = l2_policy_evict_first(), pol_out = l2_policy_evict_last();
     pdl_trigger();
     pdl_wait();
     if (lin >= rows) return;
@@ -75,7 +61,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, s
     for (int j = 0; j < MAXV; j++) {
         const int i = lane + 32 * j;
         if (i < h4) {
-            if constexpr (DELTA) v[j] = ld4(xr + 4 * i); else v[j] = ld4_hint(xr + 4 * i, pol_in);
+            v[j] = ld4(xr + 4 * i);
             if constexpr (DELTA) {
                 const uint2 d = *reinterpret_cast<const uint2*>(dr + 4 * i);
                 v[j].x += P2<BF>::to_float((uint16_t)(d.x & 0xffffu)); v[j].y += P2<BF>::to_float((uint16_t)(d.x >> 16));
@@ -106,7 +92,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, s
             uint2 pk;
             pk.x = (uint32_t)P2<BF>::from_float(o0) | ((uint32_t)P2<BF>::from_float(o1) << 16);
             pk.y = (uint32_t)P2<BF>::from_float(o2) | ((uint32_t)P2<BF>::from_float(o3) << 16);
-            st2_hint(yr + 4 * i, pk, pol_out);
+            *reinterpret_cast<uint2*>(yr + 4 * i) = pk;
         }
     }
 }
