@@ -736,6 +736,15 @@ bool clip_b200_image_batch_encode_u8(const struct clip_ctx* cctx, const struct c
     clip_ctx* c = const_cast<clip_ctx*>(cctx);
     if (!c || !c->has_vision) { set_err("no vision encoder"); return false; }
     if (!imgs || imgs->size == 0) return true;
+    if (c->replicas.size() > 1 && imgs->size >= c->replicas.size()) {
+        const int d = c->vis.proj;
+        return for_each_replica(c, imgs->size, [&](clip_ctx* r, int, size_t lo, size_t hi) {
+            if (hi == lo) return true;
+            std::lock_guard<std::mutex> lk(r->mu);
+            CK(cudaSetDevice(r->device));
+            return preprocess_chunks(r, imgs->data + lo, hi - lo, nullptr, vec + lo * d, normalize);
+        });
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     CK(cudaSetDevice(c->device));
     return preprocess_chunks(c, imgs->data, imgs->size, nullptr, vec, normalize);
@@ -1130,7 +1139,9 @@ bool clip_b200_dist_init(struct clip_ctx* c, int rank, int world, const char* re
     unsigned char id[128];
     std::string e;
     if (!dist_rendezvous_id(rank, world, rendezvous, id, e)) { set_err(e); return false; }
-    return clip_b200_dist_init_with_id(c, rank, world, id);
+    const bool ok = clip_b200_dist_init_with_id(c, rank, world, id);
+    dist_rendezvous_done(rank);
+    return ok;
 }
 
 int clip_b200_dist_rank(const struct clip_ctx* c) { return c ? c->dist.rank : 0; }

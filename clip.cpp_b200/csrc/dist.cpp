@@ -96,6 +96,14 @@ bool dist_unique_id(void* out128, std::string& err) {
 // every worker of one launcher (torchrun agent, mpirun, a test harness) shares the parent pid and MASTER_PORT, and <seq> counts
 // the rendezvous calls of this process, so repeated initialisations do not collide.  Rank 0 writes tmp + rename (atomic); readers
 // poll, and ignore files written long before this library was loaded (left over from a crashed run).
+static thread_local std::string t_last_rdzv_path;
+
+// after ncclCommInitRank has returned on rank 0 every rank has read the id (the call is collective): the file can go
+void dist_rendezvous_done(int rank) {
+    if (rank == 0 && !t_last_rdzv_path.empty()) unlink(t_last_rdzv_path.c_str());
+    t_last_rdzv_path.clear();
+}
+
 bool dist_rendezvous_id(int rank, int world, const char* rendezvous, void* id128, std::string& err) {
     (void)world;
     char path[512];
@@ -118,6 +126,7 @@ bool dist_rendezvous_id(int rank, int world, const char* rendezvous, void* id128
         fclose(f);
         if (rename(tmp, path) != 0) { err = std::string("cannot publish rendezvous file ") + path; return false; }
         memcpy(id128, rec.id, 128);
+        t_last_rdzv_path = path;
         return true;
     }
     const double deadline = (double)time(nullptr) + 600.0;

@@ -30,6 +30,7 @@ bool dist_unique_id(void* out128, std::string& err);
 // rendezvous == nullptr: derive the path from the launcher's environment (MASTER_PORT + parent pid), see dist.cpp
 bool dist_init_rank(DistComm& dc, int rank, int world, const void* id128, std::string& err);
 bool dist_rendezvous_id(int rank, int world, const char* rendezvous, void* id128, std::string& err);
+void dist_rendezvous_done(int rank);      // rank 0 removes the rendezvous file once the communicator exists
 // ---- devices mode ------------------------------------------------------------------------------------------------------
 bool dist_init_all(DistComm* comms, const int* devices, int n, std::string& err);
 void dist_destroy(DistComm& dc);

@@ -52,6 +52,12 @@ def test_devices_mode_matches_single_gpu(prod):
         assert np.allclose(got_s, want_s, rtol=1e-4)
         diff = got_x != want_x
         assert diff.mean() < 0.1 and np.allclose(got_s[diff], want_s[diff], rtol=1e-4)
+        # raw u8 images: per-GPU preprocess + encode, sharded like the f32 path
+        rng = np.random.default_rng(5)
+        u8 = [rng.integers(0, 256, (int(rng.integers(40, 200)), int(rng.integers(40, 200)), 3), dtype=np.uint8) for _ in range(19)]
+        got_u8 = prod.image_batch_encode_u8(ctx, u8)
+        host_px = np.stack([prod.preprocess(ctx, im) for im in u8])
+        assert np.array_equal(got_u8, prod.image_batch_encode(ctx, host_px))
         # fewer items than GPUs, and a single item
         assert np.array_equal(prod.image_batch_encode(ctx, imgs[:1]), want_i[:1])
         assert np.array_equal(prod.text_batch_encode(ctx, seqs[:3]), want_t[:3])
