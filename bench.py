@@ -59,7 +59,7 @@ FTYPE_ID = {"f32": 0, "f16": 1, "q4_0": 2, "q4_1": 3, "q5_0": 6, "q5_1": 7, "q8_
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm_dq_kernel from the committed `ncu --set full` captures
 # (profiles/): mean over the four layer-GEMM shapes of the configuration's micro-batch; None = not captured for this config.
-NCU_GEMM_TRAFFIC = {"headline": (502_800_000, 540_800_000, "profiles/r02_gemm.md")}
+NCU_GEMM_TRAFFIC = {"headline": (694_300_000, 742_900_000, "profiles/r02_gemm.md")}
 
 
 def log(*a):
