@@ -164,3 +164,35 @@ def test_png_decode_matches_live_reference(prod, tmp_path):
         im.save(p)
         a, b = _load_file(prod, p), _load_file(ref, p)
         assert a is not None and b is not None and np.array_equal(a, b), name
+
+
+def test_gguf_parser_survives_corrupt_files(prod, tmp_path):
+    """hostile / corrupt GGUF input must be refused, never read out of bounds.  The parser is shared by clip_model_load and
+    clip_model_quantize; the quantizer runs it without a GPU."""
+    src = model_file("tiny", "f16", prod)
+    blob = bytearray(open(src, "rb").read())
+    out = str(tmp_path / "out.gguf")
+
+    def attempt(data, name):
+        p = str(tmp_path / name)
+        with open(p, "wb") as f:
+            f.write(data)
+        return prod.quantize(p, out, 2)
+
+    assert attempt(bytes(blob), "ok.gguf")                                        # the unmodified file converts
+    for cut in (0, 3, 11, 24, 200, 5000, len(blob) // 2, len(blob) - 7):            # truncations: header, kv area, tensor infos, data
+        assert not attempt(bytes(blob[:cut]), "cut%d.gguf" % cut)
+    bad = bytearray(blob); bad[0:4] = b"XXXX"
+    assert not attempt(bytes(bad), "magic.gguf")
+    bad = bytearray(blob); bad[8:16] = (2 ** 40).to_bytes(8, "little")             # absurd tensor count
+    assert not attempt(bytes(bad), "ntensors.gguf")
+    bad = bytearray(blob); bad[16:24] = (2 ** 40).to_bytes(8, "little")            # absurd kv count
+    assert not attempt(bytes(bad), "nkv.gguf")
+    # corrupt single bytes all over the metadata: any outcome but a crash is acceptable (most flips are refused, some are harmless)
+    rng = np.random.default_rng(0)
+    meta_end = blob.find(b"v.blk.0.attn_q.weight")
+    for k in range(60):
+        bad = bytearray(blob)
+        pos = int(rng.integers(24, meta_end + 4000))
+        bad[pos] ^= int(rng.integers(1, 256))
+        attempt(bytes(bad), "flip.gguf")
