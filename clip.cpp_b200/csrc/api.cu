@@ -290,6 +290,8 @@ bool run_blocks(clip_ctx* c, Tower& tw, int nseq, int T, bool causal) {
             const int q_done = attention_tc_tiles(T) * 128;
             { Scope s(c, K_ATTN); CK(launch_attention_tc(&w.map_q128, w.qkv, &w.map_kv16, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, c->num_sms, c->stream)); }
             if (q_done < T) { Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, q_done, c->stream); }
+        } else if (c->attn_tc && attention_tc_long_supported(T, causal ? 1 : 0)) {
+            Scope s(c, K_ATTN); CK(launch_attention_tc_long(&w.map_q128, w.qkv, w.a, nseq, T, tw.heads, bf, c->num_sms, c->stream));
         } else {
             Scope s(c, K_ATTN); launch_attention(w.qkv, w.a, nseq, T, tw.heads, causal ? 1 : 0, bf, 0, c->stream);
         }
@@ -1502,7 +1504,7 @@ int clip_b200_debug_gemm(int qtype, int operand_bf16, int M, int N, int K, int e
 int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int causal, int use_legacy, const float* qkv, float* out, float* ms) {
     g_err.clear();
     if (attention_tc_init() != cudaSuccess) { set_err("attention_tc_init failed"); return 1; }
-    if (!use_legacy && !attention_tc_supported(T)) { set_err("T not supported by the tcgen05 attention kernel"); return 2; }
+    if (!use_legacy && !attention_tc_supported(T) && !attention_tc_long_supported(T, causal)) { set_err("T not supported by the tcgen05 attention kernels"); return 2; }
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceProp prop;
@@ -1530,7 +1532,8 @@ int clip_b200_debug_attention(int operand_bf16, int nseq, int T, int H, int caus
         for (int rep = 0; rep < (ms ? 3 : 1); rep++) {
             cudaEventRecord(e0, st);
             if (use_legacy) { launch_attention(d_qkv, d_out, nseq, T, H, causal, operand_bf16, 0, st); e = cudaGetLastError(); }
-            else e = launch_attention_tc(&mq, d_qkv, &m16, d_out, nseq, T, H, causal, operand_bf16, prop.multiProcessorCount, st);
+            else if (attention_tc_supported(T)) e = launch_attention_tc(&mq, d_qkv, &m16, d_out, nseq, T, H, causal, operand_bf16, prop.multiProcessorCount, st);
+            else e = launch_attention_tc_long(&mq, d_qkv, d_out, nseq, T, H, operand_bf16, prop.multiProcessorCount, st);
             cudaEventRecord(e1, st);
             if (e != cudaSuccess) break;
             if ((e = cudaStreamSynchronize(st)) != cudaSuccess) break;

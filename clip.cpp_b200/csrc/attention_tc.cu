@@ -464,6 +464,269 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attention_tc_kernel(const __gr
     if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// =====================================================================================================================================
+// Long sequences (257 < T <= 640, non-causal: ViT-L/14@336 and ViT-B/16@384 have 577 tokens): the same tcgen05 data path with an
+// ONLINE softmax over key blocks of 192.  K and V of a (sequence, head) item stay in shared memory for all of its query tiles (one
+// stage: 2 x 80 KB), each softmax group owns 256 TMEM columns: S / P of the current key block in [0, 192), the running O in
+// [192, 256).  Per key block: S = Q.K_blk^T (SS UMMA) -> block row max, new running max m, alpha = 2^((m_old - m) log2e) -> P =
+// 2^((s - m) log2e) in place over S -> O *= alpha (tcgen05.ld / st of the group's 64 O columns, after the previous block's P.V has
+// completed) -> O += P.V_blk (TS UMMA).  The two groups work on different query tiles, so one group's S / P.V fill the other's
+// softmax time.  Replaces the warp-level mma.sync kernel (attention.cu) for these shapes.
+// =====================================================================================================================================
+constexpr int LKB = 192;                                   // keys per block
+constexpr int LKV_ROWS = 640;                              // K / V rows held per item (10 TMA boxes of 64 rows)
+constexpr uint32_t LK_OFF = 0, LV_OFF = LKV_ROWS * 128, LQ_OFF = 2 * LKV_ROWS * 128;           // 0, 81920, 163840
+constexpr uint32_t LBAR_OFF = LQ_OFF + 2 * Q_BYTES;        // 196608
+constexpr uint32_t LXM_OFF = LBAR_OFF + 256;               // [parity][group][half][128] block max, then [group][half][128] row sums
+constexpr uint32_t LONG_SMEM = LXM_OFF + 2 * 2048 + 2048 + 1024;
+constexpr int LONG_THREADS = 640;
+static_assert(LV_OFF % 1024 == 0 && LQ_OFF % 1024 == 0 && (LKB * 128) % 1024 == 0, "tile alignment");
+static_assert(LONG_SMEM <= 232448, "shared memory plan");
+
+struct LParams {
+    CUtensorMap tm_q, tm_kv64;
+    uint16_t* out;
+    int T, H, nseq, ntile, nblk;
+};
+
+template <bool BF>
+__global__ void __launch_bounds__(LONG_THREADS, 1) attention_tc_long_kernel(const __grid_constant__ LParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bars = smem_base + LBAR_OFF;
+    const uint32_t kv_full = bars, kv_empty = bars + 8, q_full = bars + 16, q_empty = bars + 32, s_full = bars + 48, p_full = bars + 64,
+                   o_full = bars + 80, s_free = bars + 96;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + LBAR_OFF + 128);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntile = p.ntile, nblk = p.nblk;
+    if (threadIdx.x == 0) {
+        mbar_init(kv_full, 1); mbar_init(kv_empty, 8 * ntile);
+        for (int i = 0; i < 2; i++) {
+            mbar_init(q_full + 8 * i, 1);  mbar_init(q_empty + 8 * i, 8);
+            mbar_init(s_full + 8 * i, 1);  mbar_init(p_full + 8 * i, 8);
+            mbar_init(o_full + 8 * i, 1);  mbar_init(s_free + 8 * i, 8);
+        }
+        mbar_fence_init();
+        tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_kv64);
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();
+
+    const int hid = p.H * DH, nitems = p.nseq * p.H;
+    const int n_local = (nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int G = n_local * ntile;                                         // query tiles of this CTA; tile g belongs to group g & 1
+    const int nbox = (p.T + 63) >> 6;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (one thread): K / V of the item, then its Q tiles
+        if (elect_one()) {
+            int g = 0;
+            for (int i = 0; i < n_local; i++) {
+                const int item = (int)blockIdx.x + i * (int)gridDim.x, head = item % p.H, seq = item / p.H;
+                const int row0 = seq * p.T, c = head * DH;
+                mbar_wait(kv_empty, (i & 1) ^ 1);
+                mbar_arrive_expect_tx(kv_full, (uint32_t)(2 * nbox) * 8192u);
+                for (int b = 0; b < nbox; b++) {
+                    tma_load_3d(smem_base + LK_OFF + b * 8192, &p.tm_kv64, hid + c, b * 64, seq, kv_full);
+                    tma_load_3d(smem_base + LV_OFF + b * 8192, &p.tm_kv64, 2 * hid + c, b * 64, seq, kv_full);
+                }
+                for (int qt = 0; qt < ntile; qt++, g++) {
+                    const uint32_t sl = g & 1;
+                    mbar_wait(q_empty + 8 * sl, ((g >> 1) & 1) ^ 1);
+                    mbar_arrive_expect_tx(q_full + 8 * sl, Q_BYTES);
+                    tma_load_2d(smem_base + LQ_OFF + sl * Q_BYTES, &p.tm_q, c, row0 + qt * AQ, q_full + 8 * sl);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (one thread).  Per group the chain is strictly
+        // S(b) -> softmax -> P.V(b) -> S(b+1).  The thread POLLS both groups and issues whichever next action is ready: with a single
+        // K / V stage one group can be waiting for the next item's K / V while the other still works on the current item, and a blocking
+        // wait on the first would starve the second (and the K / V stage would never be released).
+        if (elect_one()) {
+            const uint32_t id_pv = idesc_n(BF, DH, true);
+            const int steps_g[2] = {((G + 1) >> 1) * nblk, (G >> 1) * nblk};
+            int step[2] = {0, 0};
+            bool pv_next[2] = {false, false};
+            long long t_idle = clock64();
+            while (step[0] < steps_g[0] || step[1] < steps_g[1]) {
+                bool progressed = false;
+                #pragma unroll
+                for (int grp = 0; grp < 2; grp++) {
+                    const int n = step[grp];
+                    if (n >= steps_g[grp]) continue;
+                    const int k = n / nblk, b = n - k * nblk, g = grp + 2 * k, i = g / ntile;
+                    const int nk = min(LKB, p.T - b * LKB), nk16 = (nk + 15) & ~15;
+                    if (!pv_next[grp]) {
+                        const bool ready = (b == 0) ? (mbar_try_wait(kv_full, i & 1) && mbar_try_wait(q_full + 8 * grp, k & 1) &&
+                                                       mbar_try_wait(s_free + 8 * grp, (k & 1) ^ 1))      // K / V here, Q here, previous tile's O read
+                                                    : mbar_try_wait(o_full + 8 * grp, (n - 1) & 1);        // P.V of the previous block has read P
+                        if (!ready) continue;
+                        tc_fence_after();
+                        const uint32_t id_s = idesc_n(BF, nk16, false);
+                        const uint64_t dq = umma_desc_k128(smem_base + LQ_OFF + grp * Q_BYTES), dk = umma_desc_k128(smem_base + LK_OFF + b * (LKB * 128));
+                        const uint32_t d = tmem_base + grp * S_COLS;
+                        umma_f16_init(d, dq, dk, id_s);
+                        umma_f16_acc(d, dq + 2, dk + 2, id_s);
+                        umma_f16_acc(d, dq + 4, dk + 4, id_s);
+                        umma_f16_acc(d, dq + 6, dk + 6, id_s);
+                        umma_commit(s_full + 8 * grp);
+                        pv_next[grp] = true;
+                    } else {
+                        if (!mbar_try_wait(p_full + 8 * grp, n & 1)) continue;
+                        tc_fence_after();
+                        const int npv = nk16 >> 4, nch = (nk + 31) >> 5, nch_a = (nch + 1) >> 1;
+                        const uint64_t dv = umma_desc_mn128(smem_base + LV_OFF + b * (LKB * 128));
+                        const uint32_t pa = tmem_base + grp * S_COLS, d = pa + O_COL;
+                        for (int ks = 0; ks < npv; ks++) {
+                            const int c = ks >> 1;
+                            const uint32_t pcol = (c < nch_a ? 16 * c : 32 * nch_a + 16 * (c - nch_a)) + 8 * (ks & 1);
+                            if (ks == 0 && b == 0) umma_f16_ts_init(d, pa + pcol, dv, id_pv);
+                            else umma_f16_ts_acc(d, pa + pcol, dv + (uint64_t)ks * (2048 >> 4), id_pv);
+                        }
+                        umma_commit(o_full + 8 * grp);
+                        pv_next[grp] = false;
+                        step[grp] = n + 1;
+                    }
+                    progressed = true;
+                }
+                if (progressed) t_idle = clock64();
+                else if (clock64() - t_idle > CB_WAIT_TIMEOUT_CYCLES) __trap();
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ softmax groups (TMEM lane == query row); two warps per 32-row
+        // quarter split the key chunks of a block and the output dims
+        const int grp = (warp - 4) >> 3, half = ((warp - 4) >> 2) & 1;
+        const int r = (warp & 3) * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + grp * S_COLS;
+        const float LOG2E = 1.4426950408889634f;
+        const uint32_t xm_base = smem_base + LXM_OFF, xl_base = xm_base + 4096;
+        const uint32_t xl_mine = xl_base + ((grp * 2 + half) * 128 + r) * 4, xl_other = xl_base + ((grp * 2 + (half ^ 1)) * 128 + r) * 4;
+        const int bar_id = 1 + grp * 4 + (warp & 3);
+        int n = 0;                                                          // step counter of this group (tile-major, block-minor)
+        for (int g = grp; g < G; g += 2) {
+            const int i = g / ntile, qt = g - i * ntile;
+            const int item = (int)blockIdx.x + i * (int)gridDim.x, head = item % p.H, seq = item / p.H;
+            const int qrow = qt * AQ + r;
+            const bool warp_live = (qt * AQ + (warp & 3) * 32) < p.T;
+            float m_run = -INFINITY, l = 0.f;
+            for (int b = 0; b < nblk; b++, n++) {
+                const int klim = min(LKB, p.T - b * LKB);                   // valid keys of this block
+                const int nch = (klim + 31) >> 5, nch_a = (nch + 1) >> 1;
+                const int c_lo = half ? nch_a : 0, c_hi = half ? nch : nch_a;
+                const uint32_t p_base = half ? 32 * nch_a : 0;
+                const uint32_t xm_mine = xm_base + ((((b & 1) * 2 + grp) * 2 + half) * 128 + r) * 4, xm_other = xm_base + ((((b & 1) * 2 + grp) * 2 + (half ^ 1)) * 128 + r) * 4;
+                mbar_wait(s_full + 8 * grp, n & 1);
+                tc_fence_after();
+                if (b == nblk - 1) { __syncwarp(); if (lane == 0) mbar_arrive(q_empty + 8 * grp); }     // the last S of this tile has consumed Q
+                float alpha = 1.f;
+                if (warp_live) {
+                    float m = -INFINITY;
+                    for (int c = c_lo; c < c_hi; c++) {
+                        uint32_t v[32];
+                        tmem_ld_32x32(lane_addr + c * 32, v);
+                        tmem_ld_wait();
+                        if (c * 32 + 32 <= klim) {
+                            #pragma unroll
+                            for (int i2 = 0; i2 < 32; i2++) m = fmaxf(m, __uint_as_float(v[i2]));
+                        } else {
+                            #pragma unroll
+                            for (int i2 = 0; i2 < 32; i2++)
+                                if (c * 32 + i2 < klim) m = fmaxf(m, __uint_as_float(v[i2]));
+                        }
+                    }
+                    sts32f(xm_mine, m);
+                    pair_bar_sync(bar_id);
+                    m = fmaxf(fmaxf(m, lds32f(xm_other)), m_run);
+                    if (m == -INFINITY) m = 0.f;
+                    alpha = (m_run == -INFINITY) ? 0.f : ex2f((m_run - m) * LOG2E);
+                    m_run = m;
+                    const float mb = m * LOG2E;
+                    l *= alpha;
+                    for (int c = c_lo; c < c_hi; c++) {
+                        uint32_t v[32], pk[16];
+                        tmem_ld_32x32(lane_addr + c * 32, v);
+                        tmem_ld_wait();
+                        if (c * 32 + 32 <= klim) {
+                            #pragma unroll
+                            for (int i2 = 0; i2 < 16; i2++) {
+                                const float p0 = ex2f(__uint_as_float(v[2 * i2]) * LOG2E - mb), p1 = ex2f(__uint_as_float(v[2 * i2 + 1]) * LOG2E - mb);
+                                l += p0 + p1;
+                                pk[i2] = pack2<BF>(p0, p1);
+                            }
+                        } else {
+                            #pragma unroll
+                            for (int i2 = 0; i2 < 16; i2++) {
+                                const int k0 = c * 32 + 2 * i2;
+                                const float p0 = (k0 < klim) ? ex2f(__uint_as_float(v[2 * i2]) * LOG2E - mb) : 0.f;
+                                const float p1 = (k0 + 1 < klim) ? ex2f(__uint_as_float(v[2 * i2 + 1]) * LOG2E - mb) : 0.f;
+                                l += p0 + p1;
+                                pk[i2] = pack2<BF>(p0, p1);
+                            }
+                        }
+                        tmem_st_32x16(lane_addr + p_base + (c - c_lo) * 16, pk);
+                    }
+                    // a half that owns no chunk of a short last block still holds half of the P columns the MMA reads: none (npv covers
+                    // only ceil16(klim) keys, all inside chunks [0, nch)), so nothing to clear
+                    if (b > 0) {
+                        // running output *= alpha: this half's 32 output dims (P.V of the previous block completed before S of this
+                        // block was issued, so O is quiescent)
+                        uint32_t o[32];
+                        tmem_ld_32x32(lane_addr + O_COL + half * 32, o);
+                        tmem_ld_wait();
+                        #pragma unroll
+                        for (int i2 = 0; i2 < 32; i2++) o[i2] = __float_as_uint(__uint_as_float(o[i2]) * alpha);
+                        tmem_st_32x32(lane_addr + O_COL + half * 32, o);
+                    }
+                    tmem_st_wait();
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full + 8 * grp);
+            }
+            // ---- epilogue of the tile: O / l -> global
+            mbar_wait(o_full + 8 * grp, (n - 1) & 1);
+            tc_fence_after();
+            if (warp_live) {
+                sts32f(xl_mine, l);
+                pair_bar_sync(bar_id);
+                const float inv = 1.0f / (l + lds32f(xl_other));
+                uint16_t* orow = p.out + ((size_t)seq * p.T + qrow) * hid + head * DH + half * 32;
+                uint32_t v[32];
+                tmem_ld_32x32(lane_addr + O_COL + half * 32, v);
+                tmem_ld_wait();
+                if (qrow < p.T) {
+                    #pragma unroll
+                    for (int i2 = 0; i2 < 4; i2++) {
+                        uint4 q4;
+                        q4.x = pack2<BF>(__uint_as_float(v[8 * i2 + 0]) * inv, __uint_as_float(v[8 * i2 + 1]) * inv);
+                        q4.y = pack2<BF>(__uint_as_float(v[8 * i2 + 2]) * inv, __uint_as_float(v[8 * i2 + 3]) * inv);
+                        q4.z = pack2<BF>(__uint_as_float(v[8 * i2 + 4]) * inv, __uint_as_float(v[8 * i2 + 5]) * inv);
+                        q4.w = pack2<BF>(__uint_as_float(v[8 * i2 + 6]) * inv, __uint_as_float(v[8 * i2 + 7]) * inv);
+                        *reinterpret_cast<uint4*>(orow + 8 * i2) = q4;
+                    }
+                }
+                pair_bar_sync(bar_id);                                      // the partner has read xl before the next tile rewrites it
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(s_free + 8 * grp); mbar_arrive(kv_empty); }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
 }  // namespace
 
 bool attention_tc_supported(int T) { return T >= 1 && T <= 257; }   // 256 keys on the tensor core + at most one folded in on the CUDA cores
@@ -471,10 +734,17 @@ bool attention_tc_supported(int T) { return T >= 1 && T <= 257; }   // 256 keys 
 // query tiles handled by the tcgen05 kernel (all of them since v3: a ragged last tile only keeps its live warps busy)
 int attention_tc_tiles(int T) { return (T + AQ - 1) / AQ; }
 
+// long sequences: 257 < T <= 640, non-causal (the 640 rows of K and V an item may keep in shared memory)
+bool attention_tc_long_supported(int T, int causal) { return T > 257 && T <= LKV_ROWS && !causal; }
+
 cudaError_t attention_tc_init() {
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
+    e = cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ATT_SMEM);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(attention_tc_long_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LONG_SMEM);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(attention_tc_long_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LONG_SMEM);
 }
 
 typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -482,7 +752,7 @@ typedef CUresult (*EncodeTiledFn3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // [nseq][T][3*H*64] view of the fused QKV activations, box = 64 columns x 256 tokens x 1 sequence (128-byte swizzle, zero fill)
-static bool make_kv_map(CUtensorMap* out, const void* qkv16, int nseq, int T, int H) {
+static bool make_kv_map(CUtensorMap* out, const void* qkv16, int nseq, int T, int H, unsigned box_rows = 256) {
     static EncodeTiledFn3 enc = nullptr;
     if (!enc) {
         void* f = nullptr;
@@ -493,7 +763,7 @@ static bool make_kv_map(CUtensorMap* out, const void* qkv16, int nseq, int T, in
     const cuuint64_t cols = (cuuint64_t)3 * H * DH;
     const cuuint64_t dims[3] = {cols, (cuuint64_t)T, (cuuint64_t)nseq};
     const cuuint64_t strides[2] = {cols * 2, cols * 2 * (cuuint64_t)T};
-    const cuuint32_t box[3] = {64, 256, 1}, estr[3] = {1, 1, 1};
+    const cuuint32_t box[3] = {64, box_rows, 1}, estr[3] = {1, 1, 1};
     return enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(qkv16), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -518,4 +788,23 @@ cudaError_t launch_attention_tc(const TmaMap* map_q, const void* qkv16, const Tm
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+}  // namespace cb
+
+namespace cb {
+cudaError_t launch_attention_tc_long(const TmaMap* map_q, const void* qkv16, void* out16, int nseq, int T, int H, int bf16, int num_sms,
+                                     cudaStream_t st) {
+    if (nseq <= 0) return cudaSuccess;
+    if (!attention_tc_long_supported(T, 0)) return cudaErrorInvalidValue;
+    LParams p;
+    memcpy(&p.tm_q, map_q, sizeof(CUtensorMap));
+    if (!make_kv_map(&p.tm_kv64, qkv16, nseq, T, H, 64)) return cudaErrorInvalidValue;
+    p.out = (uint16_t*)out16; p.T = T; p.H = H; p.nseq = nseq;
+    p.ntile = (T + AQ - 1) / AQ;
+    p.nblk = (T + LKB - 1) / LKB;
+    const int total = nseq * H;
+    const int grid = total < num_sms ? total : num_sms;
+    cudaError_t e = bf16 ? launch_pdl(attention_tc_long_kernel<true>, (unsigned)grid, (unsigned)LONG_THREADS, LONG_SMEM, st, 1, p)
+                         : launch_pdl(attention_tc_long_kernel<false>, (unsigned)grid, (unsigned)LONG_THREADS, LONG_SMEM, st, 1, p);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
 }  // namespace cb

@@ -38,6 +38,10 @@ int attention_tc_tiles(int T);
 cudaError_t attention_tc_init();
 cudaError_t launch_attention_tc(const TmaMap* map_q, const void* qkv16, const TmaMap* map_kv16, void* out16, int nseq, int T,
                                 int H, int causal, int bf16, int num_sms, cudaStream_t st);
+// long sequences (257 < T <= 640, non-causal; e.g. the 577 tokens of ViT-L/14@336): same data path, online softmax over 192-key blocks
+bool attention_tc_long_supported(int T, int causal);
+cudaError_t launch_attention_tc_long(const TmaMap* map_q, const void* qkv16, void* out16, int nseq, int T, int H, int bf16, int num_sms,
+                                     cudaStream_t st);
 
 // K5 head tail: out[r,:] = normalize ? v / sqrt(sum v^2) : v    (clip.cpp:1163-1166, 1448-1455)
 void launch_l2norm(const float* v, float* out, int rows, int d, int normalize, cudaStream_t st);

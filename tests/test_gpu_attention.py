@@ -109,3 +109,37 @@ def test_legacy_kernel_long_sequences(prod, T, causal):
     want = ref_attention(qkv, nseq, T, H, causal, 1)
     assert np.abs(got - want).max() / (np.abs(want).max() + 1e-6) < 2e-2
     assert one_minus_cos(got.ravel(), want.ravel()) < 1e-4
+
+
+@pytest.mark.parametrize("T,nseq,H", [(258, 3, 2), (300, 2, 3), (384, 2, 2), (385, 2, 2), (577, 2, 3), (577, 40, 16), (640, 1, 2)])
+@pytest.mark.parametrize("bf", [1, 0])
+def test_long_sequences_on_tcgen05(prod, T, nseq, H, bf):
+    """257 < T <= 640 (ViT-L/14@336: 577 tokens): the long-sequence tcgen05 kernel -- online softmax over 192-key blocks, K / V resident per
+    item, several items per CTA in the (577, 40, 16) case -- against the numpy restatement and against the warp-level kernel it replaces."""
+    rng = np.random.default_rng(T + nseq)
+    qkv = rng.standard_normal((nseq * T, 3 * H * 64)).astype(np.float32)
+    qkv[:, : H * 64] *= 0.3
+    got = run(prod, qkv, nseq, T, H, 0, bf)
+    assert np.isfinite(got).all()
+    if nseq * H <= 64:
+        want = ref_attention(qkv, nseq, T, H, 0, bf)
+        assert np.abs(got - want).max() / (np.abs(want).max() + 1e-6) < 2e-2
+        assert one_minus_cos(got.ravel(), want.ravel()) < 1e-4
+    legacy = run(prod, qkv, nseq, T, H, 0, bf, legacy=1)
+    assert np.abs(got - legacy).max() < 2e-2
+
+
+@pytest.mark.parametrize("pattern", ["ramp_up", "late_spike", "early_spike"])
+def test_long_sequences_running_max(prod, pattern):
+    """scores whose maximum moves from key block to key block: every block raises the running maximum and rescales O (ramp up), only the
+    last does (late spike), or none after the first (early spike)"""
+    rng = np.random.default_rng(3)
+    nseq, T, H = 2, 577, 2
+    qkv = (rng.standard_normal((nseq * T, 3 * H * 64)) * 0.05).astype(np.float32)
+    x = qkv.reshape(nseq, T, 3, H, 64)
+    u = np.zeros(64, np.float32); u[0] = 1.0
+    j = np.arange(T, dtype=np.float32)
+    amp = {"ramp_up": 0.2 * j, "late_spike": np.where(j == T - 3, 60.0, 0.0), "early_spike": np.where(j == 2, 60.0, 0.0)}[pattern].astype(np.float32)
+    x[:, :, 0, :, :] += u
+    x[:, :, 1, :, :] += amp[None, :, None, None] * u
+    check(prod, qkv, nseq, T, H, 0, 1, tol=3e-2)
