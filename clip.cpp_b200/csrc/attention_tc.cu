@@ -3,7 +3,7 @@
 // Reference semantics: clip.cpp:1082-1108 (text, causal) / 1363-1388 (vision); soft_max ggml.c:12201-12270.
 // One persistent CTA per SM (640 threads, all 512 TMEM columns, 180 KB shared memory) walks (sequence, head) items; K and V of an
 // item stay in shared memory for all of its 128-query tiles and the next item's K/V are prefetched into the second stage:
-//   warp 0      TMA: K and V boxes [256 (+16) keys x 64] straight out of the fused QKV activation matrix (row stride 3*hidden),
+//   warp 0      TMA: K and V boxes [256 (+16) keys x 64] straight out of the fused QKV activation matrix (3-D view, row stride 3*hidden),
 //               the item's LAST query row when T % 128 == 1, and its Q boxes [128 x 64] (two slots)
 //   warp 1      one elected thread: S[128 x <=256] = Q.K^T (SS form, 4 UMMA k-steps) into TMEM buffer g&1, then
 //               O[128 x 64] = P.V (TS form: A = P from TMEM, B = V taken MN-major from the same [key][dh] tile).  S of tile g+1
@@ -18,7 +18,10 @@
 //   warps 2, 3  the 257th QUERY row (T % 128 == 1) on the CUDA cores, alternating items: 257 dot products, softmax, 257 axpys out
 //               of the K/V tiles in shared memory -- a third, 127/128-empty tensor-core tile would cost a full pipeline slot.
 //   warp 2      also TMEM alloc (per buffer: S columns [0,256); P [0,64) and [128,192) in place; O [192,256) once S is dead)
-// HBM traffic: Q, K, V read exactly once, O written once.  Limits: head_dim 64, T <= 257.
+// HBM traffic: Q, K, V read exactly once, O written once.  Limits: head_dim 64, T <= 257 for this kernel; attention_tc_long_kernel
+// further down covers 257 < T <= 640 (non-causal) with an online softmax over 192-key blocks.
+// K / V boxes come through a per-launch 3-D tensor map [sequence][token][column]: rows past a sequence's T tokens are zero-filled by
+// TMA, so padded keys can never inject another sequence's (or stale) NaN / Inf into P.V.  The MMA issuer is one elected thread.
 // History (ViT-L/14, 82 images per launch): mma.sync flash kernel 148 us -> v3 (serial phases, 2 CTAs/SM) 88 us -> v4 (K/V resident,
 // ping-pong groups) 78 us -> this kernel 65 us; profiles/r01_attention.md has the stall breakdown.  Per item the kernel needs
 // ~4.1 K MUFU cycles, ~5 K tcgen05.ld cycles and ~5.8 K issue cycles per scheduler; a single-pass variant with a lazily raised

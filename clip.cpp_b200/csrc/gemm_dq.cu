@@ -11,20 +11,26 @@
 // operand from TMEM (tcgen05.mma "TS" form).  Shared memory then carries only the activation tile (TMA in, UMMA out) and
 // the packed 4-8 bit blocks -- it was the binding resource of the earlier smem->smem version.
 //
-// Warp roles (persistent CTA, 1 per SM, 512 threads; 256 for unquantized f16 weights):
-//   warp 0      X producer: activation box [192 tokens x 64 k] (UTMALDG, 128B swizzle)            -> x_full[s]
+// Warp roles (persistent CTA, 1 per SM, 512 threads; 256 for unquantized f16 weights).  For N % 256 == 0 (every layer GEMM) a CTA PAIR
+// (cluster of 2) owns a [256 features x 192 tokens] tile and the leader issues cta_group::2 UMMAs (M = 256):
+//   warp 0      X producer: activation box (UTMALDG, 128B swizzle); pair form: each CTA loads its HALF of the token tile (96 rows,
+//               12 KB per k-block) into a 12-deep ring, bytes credited to the leader's barrier                         -> x_full[s]
 //   warp 3      Q producer: ONE 1-D bulk copy (UBLKCP) per k-block of the packed 32-weight blocks + scales of
-//               the [128 x 64] weight tile (wpack.h); runs up to 8 k-blocks ahead                  -> q_full[s]
+//               the [128 x 64] weight tile (wpack.h); runs up to 8 k-blocks ahead                                      -> q_full[s]
 //   warps 8-15  unpack, 2 groups x 4 warps (one warp per TMEM lane quarter); group g owns k-blocks i = g (mod 2):
 //               thread = one weight row x 64 k: ld.shared packed q4_0/q4_1/q5_0/q5_1/q8_0 -> 32 registers of 16-bit
-//               pairs -> tcgen05.st.32x32b.x32 into A stage (i mod 4)                               -> a_full[j]
-//   warp 1      one elected thread issues tcgen05.mma (M128 N192 K16, kind::f16, A from TMEM, B from smem), fp32
-//               accumulators in TMEM; tcgen05.commit releases the X / A stages and signals the epilogue
-//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / scale / GELU -> coalesced global stores;
+//               pairs (one LOP3 + one sub + one mul per pair for q4_0) -> tcgen05.st.32x32b.x32 into A stage (i mod 4)  -> a_full[j]
+//   warp 1      ONE elected thread runs the whole issue loop: tcgen05.mma (N192 K16, kind::f16, A from TMEM, B from smem), fp32
+//               accumulators in TMEM; tcgen05.commit releases the X / A stages and signals the epilogue.  This thread is the
+//               kernel's critical path (it shares its scheduler with an epilogue warp and two unpack warps): its loop is unrolled
+//               over lcm(X ring, A ring) k-blocks so stage indices and barrier addresses are compile-time constants
+//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / scale / GELU -> 2-byte (or fp32) st.shared into a [32 tokens x 32 features]
+//               block -> ONE TMA tensor store per block, or a TMA tensor REDUCE-ADD into the fp32 residual stream (EPI_REDADD32);
 //               double-buffered accumulators (2 x 192 TMEM columns) overlap it with the next tile's MMAs
 //   warp 2      TMEM alloc / dealloc   (TMEM map: acc0 [0,192) acc1 [192,384) A stages [384 + 32 j), j < 4)
 //
-// Unquantized (f16 / f32-rounded-to-f16) weights use the plain SS form: warp 0 TMA-loads X and W tiles.
+// Unquantized (f16 / f32-rounded-to-f16) weights use the plain SS form: warp 0 TMA-loads X and W tiles, direct global stores.
+// gemm_dq2_kernel below is the "wide" form ([256 x 384] super-tiles, both accumulators live): measured slower, opt-in only.
 // Algorithmic bytes per launch: packed W once + X once + Y once; FLOPs = 2*M*N*K.
 #include <cuda.h>
 #include <stdlib.h>

@@ -1,5 +1,5 @@
 // kernels.cu -- the memory-bound kernels around the GEMMs: LayerNorm (K2), im2col (K0a), embedding assembly (K4),
-// L2-normalise (K5), zero-shot scoring, plus a scalar debug GEMM.  All are HBM-bound streaming kernels: one warp per
+// L2-normalise (K5), plus a scalar debug GEMM (scoring lives in search.cu).  All are HBM-bound streaming kernels: one warp per
 // row, 128-bit coalesced loads, warp-shuffle reductions, no shared memory.
 #include <stdlib.h>
 #include <string.h>
