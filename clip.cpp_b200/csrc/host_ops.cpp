@@ -387,8 +387,8 @@ bool quantize_file(const char* inp, const char* outp, int itype, std::string& er
 }
 
 // ---------------------------------------------------------------------------------------------------
-// image files: binary PPM (P6, maxval 255) and 24-bit uncompressed BMP.  (The reference uses stb_image,
-// clip.cpp:709-726; JPEG/PNG decoding is host-side convenience outside the hot path and is not reproduced.)
+// image files (the reference uses stb_image, clip.cpp:709-726): JPEG (jpeg.cpp), PNG, binary PPM (P6, maxval 255) and 24-bit
+// uncompressed BMP, each decoded to the same 3-channel pixels stb_image returns.
 // ---------------------------------------------------------------------------------------------------
 // PNG (the lossless format the reference's callers use besides JPEG; the reference decodes through stb_image, clip.cpp:709-726, and asks
 // for 3 channels: alpha is dropped, grey is replicated, 16-bit samples keep their high byte).  Non-interlaced, colour types 0/2/3/4/6,
@@ -457,6 +457,7 @@ bool load_image_file(const char* fname, std::vector<uint8_t>& rgb, int& nx, int&
     if (!f) return false;
     std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     if (buf.size() >= 8 && buf[0] == 0x89 && buf[1] == 'P' && buf[2] == 'N' && buf[3] == 'G') return decode_png(buf, rgb, nx, ny);
+    if (buf.size() >= 4 && buf[0] == 0xFF && buf[1] == 0xD8) return decode_jpeg(buf.data(), buf.size(), rgb, nx, ny);
     if (buf.size() >= 2 && buf[0] == 'P' && buf[1] == '6') {
         size_t p = 2;
         int vals[3], got = 0;

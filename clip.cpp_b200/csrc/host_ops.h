@@ -41,5 +41,7 @@ bool preprocess_image(const uint8_t* src, int nx, int ny, int out_size, const fl
 bool quantize_file(const char* inp, const char* out, int itype, std::string& err);
 
 bool load_image_file(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny);
+// jpeg.cpp: baseline / progressive Huffman JPEG -> interleaved RGB, pixels identical to the reference's stb_image path
+bool decode_jpeg(const uint8_t* data, size_t size, std::vector<uint8_t>& rgb, int& nx, int& ny);
 
 }  // namespace cb

@@ -111,9 +111,11 @@ void clip_image_f32_clean(struct clip_image_f32 * res);
 void clip_image_u8_free(struct clip_image_u8 * img);
 void clip_image_f32_free(struct clip_image_f32 * res);
 
-/* clip.h:87, clip.cpp:709-726 -- the reference decodes with stb_image; this library decodes PNG (non-interlaced, 8 / 16 bits per
- * sample, bit-identical to stb_image's 3-channel output), binary PPM (P6) and 24-bit BMP.  JPEG / GIF return false with an explicit
- * message in clip_b200_last_error (decoding is outside the hot path). */
+/* clip.h:87, clip.cpp:709-726 -- the reference decodes with stb_image; this library has its own decoders for JPEG (Huffman baseline and
+ * progressive, 8-bit, grey / YCbCr / RGB / CMYK / YCCK, any integer sampling ratio, restart intervals), PNG (non-interlaced, 8 / 16 bits
+ * per sample), binary PPM (P6) and 24-bit BMP.  Each returns the same 3-channel pixels as stb_image, byte for byte (JPEG included: the
+ * inverse DCT, chroma up-sampling and colour conversion follow stb_image's integer arithmetic; tests/golden/jpeg).  GIF / TGA / PSD /
+ * HDR and arithmetic-coded or 12-bit JPEG return false with an explicit message in clip_b200_last_error. */
 bool clip_image_load_from_file(const char * fname, struct clip_image_u8 * img);
 
 /* clip.h:88, clip.cpp:797-927 -- host side PIL-style bicubic resize + centre crop + normalise */
