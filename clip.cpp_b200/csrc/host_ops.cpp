@@ -453,9 +453,17 @@ static bool decode_png(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rg
 }
 
 bool load_image_file(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny) {
-    std::ifstream f(fname, std::ios::binary);
+    FILE* f = fopen(fname, "rb");
     if (!f) return false;
-    std::vector<uint8_t> buf((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    std::vector<uint8_t> buf;
+    if (fseek(f, 0, SEEK_END) == 0) {
+        const long len = ftell(f);
+        if (len > 0) buf.resize((size_t)len);
+    }
+    rewind(f);
+    const size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), f);
+    fclose(f);
+    if (got != buf.size() || buf.empty()) return false;
     if (buf.size() >= 8 && buf[0] == 0x89 && buf[1] == 'P' && buf[2] == 'N' && buf[3] == 'G') return decode_png(buf, rgb, nx, ny);
     if (buf.size() >= 4 && buf[0] == 0xFF && buf[1] == 0xD8) return decode_jpeg(buf.data(), buf.size(), rgb, nx, ny);
     if (buf.size() >= 2 && buf[0] == 'P' && buf[1] == '6') {

@@ -193,7 +193,7 @@ def test_jpeg_decode_matches_live_reference(prod, tmp_path):
     ref = bd.ClipLib(ref_run.REF_LIB)
     p = str(tmp_path / "t.jpg")
     n = 0
-    for (w, h) in [(1, 1), (8, 8), (15, 9), (33, 17), (100, 75), (224, 224)]:
+    for (w, h) in [(1, 1), (8, 8), (15, 9), (33, 17), (100, 75), (224, 224), (1234, 901)]:       # the last one is > 1 MP: threaded IDCT / colour rows
         y, x = np.mgrid[0:h, 0:w]
         pics = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8),
                 np.stack([np.sin(x / 3.0) * 127 + 128, np.cos(y / 5.0) * 127 + 128, ((x // 4 + y // 4) % 2) * 255], -1).astype(np.uint8)]
