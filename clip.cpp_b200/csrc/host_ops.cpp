@@ -267,42 +267,54 @@ bool preprocess_geometry(int nx, int ny, int S, int* nx3, int* ny3) {
 
 namespace {
 typedef ResizeTaps Taps;
-inline Taps make_taps(int in_size, int out_size) { return resize_taps(in_size, out_size, 0, out_size); }
 inline float clamp255(double v) { return std::min(std::max((float)v, 0.0f), 255.0f); }
 }  // namespace
 
+// Only what the centre crop keeps is computed: output columns [xo, xo+S) of the horizontal pass, for the input rows the vertical taps
+// of output rows [yo, yo+S) touch.  Every kept sample is produced by the same sequence of double operations as in the reference
+// (taps in ascending order into one accumulator, clamp, float), so the result does not change -- the loops are only arranged so that
+// the three channels (horizontal) and a whole row of samples (vertical) are independent accumulators side by side.
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target_clones("avx2", "default")))      // wider lanes for the row accumulators; no FMA contraction either way
+#endif
 bool preprocess_image(const uint8_t* src, int nx, int ny, int S, const float mean[3], const float stdv[3], float* dst) {
     int nx3 = 0, ny3 = 0;
     if (!src || !preprocess_geometry(nx, ny, S, &nx3, &ny3)) return false;
-    const Taps th = make_taps(nx, nx3), tv = make_taps(ny, ny3);
-    std::vector<float> tmp((size_t)3 * nx3 * ny), res((size_t)3 * nx3 * ny3);
-    for (int y = 0; y < ny; y++)
-        for (int xx = 0; xx < nx3; xx++) {
+    const int xo = (nx3 - S) / 2, yo = (ny3 - S) / 2;
+    const Taps th = resize_taps(nx, nx3, xo, S), tv = resize_taps(ny, ny3, yo, S);
+    const int r_lo = tv.lo[0], r_hi = tv.lo[S - 1] + tv.cnt[S - 1];           // tap windows move monotonically with the output row
+    const size_t row_len = (size_t)3 * S;
+    std::vector<float> tmp((size_t)(r_hi - r_lo) * row_len);
+    for (int y = r_lo; y < r_hi; y++) {
+        const uint8_t* row = src + (size_t)3 * nx * y;
+        float* out = &tmp[(size_t)(y - r_lo) * row_len];
+        for (int xx = 0; xx < S; xx++) {
             const double* k = &th.k[(size_t)xx * th.ksize];
-            const int lo = th.lo[xx], cnt = th.cnt[xx];
-            for (int c = 0; c < 3; c++) {
-                double acc = 0.0;
-                for (int x = 0; x < cnt; x++) acc += (double)src[3 * ((size_t)y * nx + (x + lo)) + c] * k[x];
-                tmp[3 * ((size_t)y * nx3 + xx) + c] = clamp255(acc);
+            const uint8_t* p = row + (size_t)3 * th.lo[xx];
+            const int cnt = th.cnt[xx];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int x = 0; x < cnt; x++, p += 3) {
+                const double w = k[x];
+                a0 += (double)p[0] * w; a1 += (double)p[1] * w; a2 += (double)p[2] * w;
             }
+            out[3 * xx] = clamp255(a0); out[3 * xx + 1] = clamp255(a1); out[3 * xx + 2] = clamp255(a2);
         }
-    for (int yy = 0; yy < ny3; yy++) {
+    }
+    std::vector<double> acc(row_len);
+    for (int yy = 0; yy < S; yy++) {
         const double* k = &tv.k[(size_t)yy * tv.ksize];
         const int lo = tv.lo[yy], cnt = tv.cnt[yy];
-        for (int x = 0; x < nx3; x++)
-            for (int c = 0; c < 3; c++) {
-                double acc = 0.0;
-                for (int y = 0; y < cnt; y++) acc += (double)tmp[3 * ((size_t)(y + lo) * nx3 + x) + c] * k[y];
-                res[3 * ((size_t)yy * nx3 + x) + c] = clamp255(acc);
-            }
-    }
-    const int xo = (nx3 - S) / 2, yo = (ny3 - S) / 2;
-    for (int y = 0; y < S; y++)
+        std::fill(acc.begin(), acc.end(), 0.0);
+        double* __restrict a = acc.data();
+        for (int y = 0; y < cnt; y++) {
+            const float* __restrict row = &tmp[(size_t)(lo + y - r_lo) * row_len];
+            const double w = k[y];
+            for (size_t i = 0; i < row_len; i++) a[i] += (double)row[i] * w;
+        }
+        float* out = dst + (size_t)yy * row_len;
         for (int x = 0; x < S; x++)
-            for (int c = 0; c < 3; c++) {
-                const float v = res[3 * ((size_t)(y + yo) * nx3 + (x + xo)) + c];
-                dst[3 * ((size_t)y * S + x) + c] = ((v / 255.0f) - mean[c]) / stdv[c];
-            }
+            for (int c = 0; c < 3; c++) out[3 * x + c] = ((clamp255(acc[3 * x + c]) / 255.0f) - mean[c]) / stdv[c];
+    }
     return true;
 }
 
