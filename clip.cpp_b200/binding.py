@@ -386,6 +386,21 @@ class ClipLib:
             self.lib.clip_image_f32_clean(C.byref(res[i]))
         return out
 
+    def batch_preprocess(self, ctx, images, n_threads: int = 4) -> np.ndarray:
+        """clip_image_batch_preprocess (clip.h:95-96): the reference's batch call -> [n, S, S, 3] float32.  Host threads by default,
+        the GPU when CLIP_B200_PREPROCESS=device is set in the environment."""
+        batch, keep = self._u8_batch(images)
+        res = (clip_image_f32 * len(images))()
+        outb = clip_image_f32_batch(res, len(images))
+        self.lib.clip_image_batch_preprocess(ctx, n_threads, C.byref(batch), C.byref(outb))
+        if any(not res[i].data for i in range(len(images))):
+            raise RuntimeError("clip_image_batch_preprocess failed: " + self.last_error())
+        s = res[0].nx
+        out = np.stack([np.ctypeslib.as_array(res[i].data, shape=(s, s, 3)).copy() for i in range(len(images))])
+        for i in range(len(images)):
+            self.lib.clip_image_f32_clean(C.byref(res[i]))
+        return out
+
     def preprocess(self, ctx, img_u8: np.ndarray) -> np.ndarray:
         """img_u8: [ny, nx, 3] uint8 -> [S, S, 3] float32 (clip.cpp:797-927 semantics)."""
         img_u8 = np.ascontiguousarray(img_u8, np.uint8)

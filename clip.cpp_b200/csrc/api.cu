@@ -699,6 +699,16 @@ bool clip_image_preprocess(const struct clip_ctx* ctx, const struct clip_image_u
 
 void clip_image_batch_preprocess(const struct clip_ctx* ctx, const int n_threads, const struct clip_image_u8_batch* in,
                                  struct clip_image_f32_batch* out) {
+    // CLIP_B200_PREPROCESS=device: the same call runs K6a/K6b on the GPU (bit-identical results, new[]-owned buffers as below); a
+    // failure is reported and leaves the outputs empty -- no silent detour through the host loop
+    const char* where = getenv("CLIP_B200_PREPROCESS");
+    if (where && strcmp(where, "device") == 0 && in->size > 0) {
+        if (!clip_b200_image_batch_preprocess_device(ctx, in, out)) {
+            fprintf(stderr, "clip_image_batch_preprocess (device): %s\n", clip_b200_last_error());
+            for (size_t i = 0; i < in->size; i++) { out->data[i].data = nullptr; out->data[i].size = 0; }
+        }
+        return;
+    }
     out->size = in->size;
     const size_t n = in->size;
     int nt = std::max(1, std::min<int>(n_threads, (int)n));

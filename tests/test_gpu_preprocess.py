@@ -41,6 +41,17 @@ def test_device_preprocess_is_bit_identical_to_host(prod, ctx):
         assert np.array_equal(host, dev[i]), (SIZES[i], np.abs(host - dev[i]).max())
 
 
+def test_reference_batch_call_on_host_threads_and_on_device(prod, ctx, monkeypatch):
+    """clip_image_batch_preprocess (clip.h:95-96) as a reference caller uses it: host threads by default, the same call on the GPU
+    with CLIP_B200_PREPROCESS=device -- identical buffers either way."""
+    imgs = _images(SIZES, 5)
+    want = np.stack([prod.preprocess(ctx, im) for im in imgs])
+    monkeypatch.delenv("CLIP_B200_PREPROCESS", raising=False)
+    assert np.array_equal(prod.batch_preprocess(ctx, imgs, n_threads=3), want)
+    monkeypatch.setenv("CLIP_B200_PREPROCESS", "device")
+    assert np.array_equal(prod.batch_preprocess(ctx, imgs, n_threads=3), want)
+
+
 def test_fused_u8_encode_equals_host_preprocess_plus_encode(prod, ctx):
     imgs = _images(SIZES * 3, 2)
     fused = prod.image_batch_encode_u8(ctx, imgs)
