@@ -260,3 +260,20 @@ def test_gguf_parser_survives_corrupt_files(prod, tmp_path):
         pos = int(rng.integers(24, meta_end + 4000))
         bad[pos] ^= int(rng.integers(1, 256))
         attempt(bytes(bad), "flip.gguf")
+
+
+def test_reference_examples_link_unchanged_and_fail_loudly_without_a_gpu(prod):
+    """oracle/Makefile `examples`: the reference's examples/{simple.c,main.cpp,zsl.cpp,extract.cpp} compile and link against
+    include/clip.h + libclip_b200.so as they are (the drop-in claim at the source level).  On a box without a GPU the resulting program
+    must stop at clip_model_load with the library's message -- there is no CPU path to fall into."""
+    import subprocess
+    from _util import ROOT
+    bins = [os.path.join(ROOT, "oracle", "_ref", b) for b in ("ex_simple_b200", "ex_main_b200", "ex_zsl_b200", "ex_extract_b200")]
+    if not all(os.path.exists(b) for b in bins):
+        pytest.skip("oracle/_ref/ex_*_b200 not built (needs /root/reference: make -C oracle examples)")
+    if prod.lib.clip_b200_cuda_device_count() > 0:
+        pytest.skip("a GPU is present: tests/test_gpu_zz_examples.py runs the programs for real")
+    model = model_file("tiny", "f16", prod)
+    r = subprocess.run([bins[1], "-m", model, "--text", "apple", "--image", os.path.join(JPEG_GOLDEN, "pil_444_base.jpg")],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no CUDA device" in (r.stdout + r.stderr), (r.returncode, r.stdout[-300:], r.stderr[-300:])
