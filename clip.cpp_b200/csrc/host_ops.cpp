@@ -402,9 +402,9 @@ bool quantize_file(const char* inp, const char* outp, int itype, std::string& er
 // image files (the reference uses stb_image, clip.cpp:709-726): JPEG (jpeg.cpp), PNG, binary PPM (P6, maxval 255) and 24-bit
 // uncompressed BMP, each decoded to the same 3-channel pixels stb_image returns.
 // ---------------------------------------------------------------------------------------------------
-// PNG (the lossless format the reference's callers use besides JPEG; the reference decodes through stb_image, clip.cpp:709-726, and asks
-// for 3 channels: alpha is dropped, grey is replicated, 16-bit samples keep their high byte).  Non-interlaced, colour types 0/2/3/4/6,
-// 8 or 16 bits per sample (palette: 8).  zlib does the inflate; the result is bit-identical to what stb_image returns.
+// PNG (the reference decodes through stb_image, clip.cpp:709-726, and asks for 3 channels: alpha is dropped, grey is replicated, grey of
+// 1 / 2 / 4 bits is scaled to 0..255, 16-bit samples keep their high byte).  Colour types 0/2/3/4/6, every legal bit depth, plain and
+// Adam7-interlaced.  zlib does the inflate; the result is bit-identical to what stb_image returns.
 static bool decode_png(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rgb, int& nx, int& ny) {
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (buf.size() < 8 + 25 || memcmp(buf.data(), sig, 8) != 0) return false;
@@ -423,42 +423,75 @@ static bool decode_png(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rg
         else if (!memcmp(tag, "IEND", 4)) break;
         p += 12 + (size_t)len;
     }
-    if (w == 0 || h == 0 || w > 65535 || h > 65535 || interlace != 0) return false;
+    if (w == 0 || h == 0 || w > 65535 || h > 65535 || interlace > 1) return false;
     int ch;
     switch (ctype) { case 0: ch = 1; break; case 2: ch = 3; break; case 3: ch = 1; break; case 4: ch = 2; break; case 6: ch = 4; break; default: return false; }
-    if (!(depth == 8 || (depth == 16 && ctype != 3))) return false;
-    const size_t bps = (size_t)depth / 8, bpp = bps * ch, stride = bpp * w;
-    std::vector<uint8_t> raw((stride + 1) * h);
+    const bool small = depth == 1 || depth == 2 || depth == 4;                 // packed samples: grey and palette only
+    if (!(depth == 8 || (depth == 16 && ctype != 3) || (small && (ctype == 0 || ctype == 3)))) return false;
+    const size_t bits_pp = (size_t)depth * ch;
+    const size_t bps = depth == 16 ? 2 : 1, bpp = bits_pp >= 8 ? bits_pp / 8 : 1;   // bpp: the distance the filters look back
+    // Adam7 (PNG spec 8.2): pass p holds the pixels (x0 + i*dx, y0 + j*dy); a plain image is one pass covering everything
+    static const int ax0[7] = {0, 4, 0, 2, 0, 1, 0}, ay0[7] = {0, 0, 4, 0, 2, 0, 1}, adx[7] = {8, 8, 4, 4, 2, 2, 1}, ady[7] = {8, 8, 8, 4, 4, 2, 2};
+    struct Pass { uint32_t x0, y0, dx, dy, pw, ph; size_t stride; };
+    std::vector<Pass> passes;
+    size_t total = 0;
+    for (int p = 0; p < (interlace ? 7 : 1); p++) {
+        Pass q;
+        if (interlace) { q.x0 = ax0[p]; q.y0 = ay0[p]; q.dx = adx[p]; q.dy = ady[p]; }
+        else { q.x0 = q.y0 = 0; q.dx = q.dy = 1; }
+        if (w <= q.x0 || h <= q.y0) continue;                                   // empty pass: no bytes in the stream
+        q.pw = (w - q.x0 + q.dx - 1) / q.dx;
+        q.ph = (h - q.y0 + q.dy - 1) / q.dy;
+        q.stride = (q.pw * bits_pp + 7) / 8;
+        total += (q.stride + 1) * q.ph;
+        passes.push_back(q);
+    }
+    std::vector<uint8_t> raw(total);
     uLongf got = (uLongf)raw.size();
     if (uncompress(raw.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != raw.size()) return false;
-    std::vector<uint8_t> prev(stride, 0), cur(stride);
+    const int scale = depth == 1 ? 255 : (depth == 2 ? 85 : 17), mask = (1 << depth) - 1;
     rgb.resize((size_t)w * h * 3);
-    for (uint32_t y = 0; y < h; y++) {
-        const uint8_t ft = raw[(stride + 1) * y];
-        const uint8_t* in = &raw[(stride + 1) * y + 1];
-        for (size_t i = 0; i < stride; i++) {
-            const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
-            int pred;
-            switch (ft) {
-            case 0: pred = 0; break;
-            case 1: pred = a; break;
-            case 2: pred = b; break;
-            case 3: pred = (a + b) >> 1; break;
-            case 4: { const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); } break;
-            default: return false;
+    size_t at = 0;
+    std::vector<uint8_t> prev, cur;
+    for (const Pass& q : passes) {
+        prev.assign(q.stride, 0);
+        cur.resize(q.stride);
+        for (uint32_t y = 0; y < q.ph; y++) {
+            const uint8_t ft = raw[at];
+            const uint8_t* in = &raw[at + 1];
+            at += q.stride + 1;
+            for (size_t i = 0; i < q.stride; i++) {
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+                int pred;
+                switch (ft) {
+                case 0: pred = 0; break;
+                case 1: pred = a; break;
+                case 2: pred = b; break;
+                case 3: pred = (a + b) >> 1; break;
+                case 4: { const int pa = abs(b - c), pb = abs(a - c), pc = abs(a + b - 2 * c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); } break;
+                default: return false;
+                }
+                cur[i] = (uint8_t)(in[i] + pred);
             }
-            cur[i] = (uint8_t)(in[i] + pred);
-        }
-        uint8_t* out = &rgb[(size_t)y * w * 3];
-        for (uint32_t x = 0; x < w; x++) {
-            const uint8_t* px = &cur[x * bpp];          // 16-bit samples are big-endian: the first byte is the high byte stb keeps
-            switch (ctype) {
-            case 0: case 4: out[3 * x] = out[3 * x + 1] = out[3 * x + 2] = px[0]; break;
-            case 2: case 6: out[3 * x] = px[0]; out[3 * x + 1] = px[bps]; out[3 * x + 2] = px[2 * bps]; break;
-            case 3: { const size_t k = (size_t)px[0] * 3; if (k + 3 > pal.size()) return false; out[3 * x] = pal[k]; out[3 * x + 1] = pal[k + 1]; out[3 * x + 2] = pal[k + 2]; } break;
+            uint8_t* row = &rgb[(size_t)(q.y0 + y * q.dy) * w * 3];
+            for (uint32_t x = 0; x < q.pw; x++) {
+                uint8_t* out = row + (size_t)(q.x0 + x * q.dx) * 3;
+                if (small) {
+                    const size_t bit = (size_t)x * depth;
+                    const int v = (cur[bit >> 3] >> (8 - depth - (bit & 7))) & mask;
+                    if (ctype == 0) out[0] = out[1] = out[2] = (uint8_t)(v * scale);
+                    else { const size_t k = (size_t)v * 3; if (k + 3 > pal.size()) return false; out[0] = pal[k]; out[1] = pal[k + 1]; out[2] = pal[k + 2]; }
+                    continue;
+                }
+                const uint8_t* px = &cur[x * (bits_pp / 8)];       // 16-bit samples are big-endian: the first byte is the high byte stb keeps
+                switch (ctype) {
+                case 0: case 4: out[0] = out[1] = out[2] = px[0]; break;
+                case 2: case 6: out[0] = px[0]; out[1] = px[bps]; out[2] = px[2 * bps]; break;
+                case 3: { const size_t k = (size_t)px[0] * 3; if (k + 3 > pal.size()) return false; out[0] = pal[k]; out[1] = pal[k + 1]; out[2] = pal[k + 2]; } break;
+                }
             }
+            prev.swap(cur);
         }
-        prev.swap(cur);
     }
     nx = (int)w; ny = (int)h;
     return true;
