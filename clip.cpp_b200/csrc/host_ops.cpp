@@ -13,6 +13,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <new>
 #include <fstream>
 
 #include "gguf.hpp"
@@ -423,7 +424,7 @@ static bool decode_png(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rg
         else if (!memcmp(tag, "IEND", 4)) break;
         p += 12 + (size_t)len;
     }
-    if (w == 0 || h == 0 || w > 65535 || h > 65535 || interlace > 1) return false;
+    if (w == 0 || h == 0 || w > 65535 || h > 65535 || (uint64_t)w * h > (1ull << 28) || interlace > 1) return false;
     int ch;
     switch (ctype) { case 0: ch = 1; break; case 2: ch = 3; break; case 3: ch = 1; break; case 4: ch = 2; break; case 6: ch = 4; break; default: return false; }
     const bool small = depth == 1 || depth == 2 || depth == 4;                 // packed samples: grey and palette only
@@ -497,7 +498,16 @@ static bool decode_png(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rg
     return true;
 }
 
+static bool load_image_file_impl(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny);
 bool load_image_file(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny) {
+    try {
+        return load_image_file_impl(fname, rgb, nx, ny);
+    } catch (const std::bad_alloc&) {          // a header announcing more pixels than there is memory: refuse, do not unwind through the C ABI
+        return false;
+    }
+}
+
+static bool load_image_file_impl(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny) {
     FILE* f = fopen(fname, "rb");
     if (!f) return false;
     std::vector<uint8_t> buf;
