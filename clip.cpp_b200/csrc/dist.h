@@ -43,7 +43,7 @@ bool dist_group_start(std::string& err);
 bool dist_group_end(std::string& err);
 int dist_nccl_version();
 
-// contiguous, balanced shard r of n items over w workers: [n*r/w, n*(r+1)/w)  (clip.cpp_b200/dist_util.py: shard_bounds)
+// contiguous, balanced shard r of n items over w workers: [n*r/w, n*(r+1)/w)  (mirrored for the CPU tests by tests/gloo_mirror.py: shard_bounds)
 inline void shard_bounds(size_t n, int r, int w, size_t& lo, size_t& hi) {
     lo = n * (size_t)r / (size_t)w;
     hi = n * (size_t)(r + 1) / (size_t)w;

@@ -1,6 +1,7 @@
-"""Multi-GPU plumbing for the encode path: one process per GPU, images / sequences shard
-embarrassingly, weights are replicated, and the ONLY exchange is one all-gather of the final embeddings per call
-(NCCL over NVLink on GPUs; the same code runs on gloo for the CPU tests).  torch.distributed is plumbing only."""
+"""Test-only gloo mirror of the library's multi-GPU data flow (the product is csrc/dist.{h,cpp}: NCCL through dlopen,
+no torch).  Same shard rule, same single all-gather, same sharded zero-shot -- run on torch.distributed/gloo by
+tests/test_distributed_cpu.py so the N > 1 logic is exercised on a box without GPUs, and compared with the library's own
+clip_b200_debug_shard_bounds."""
 from __future__ import annotations
 
 

@@ -5,7 +5,7 @@ import socket
 import numpy as np
 import pytest
 
-import dist_util as du
+import gloo_mirror as du
 
 
 def test_shard_bounds_cover_everything():
