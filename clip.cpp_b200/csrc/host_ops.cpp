@@ -498,6 +498,94 @@ static bool decode_png(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rg
     return true;
 }
 
+// BMP as stb_image reads it (3 channels requested, so an alpha channel is simply dropped): OS/2 and Windows V3/V4/V5 headers,
+// 1 / 4 / 8-bit palettes, 24-bit BGR, 16 / 32-bit with the default or BI_BITFIELDS masks (a field of n < 8 bits widens by repeating its
+// bits), bottom-up or top-down.  RLE-compressed files are refused, as in the reference.
+static bool decode_bmp(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rgb, int& nx, int& ny) {
+    auto u16 = [&](size_t o) -> uint32_t { return o + 2 <= buf.size() ? (uint32_t)buf[o] | ((uint32_t)buf[o + 1] << 8) : 0u; };
+    auto u32 = [&](size_t o) -> uint32_t { return u16(o) | (u16(o + 2) << 16); };
+    const uint32_t offs = u32(10), hsz = u32(14);
+    if (!(hsz == 12 || hsz == 40 || hsz == 56 || hsz == 108 || hsz == 124)) return false;
+    int64_t w, h;
+    uint32_t planes, bpp, comp = 0;
+    if (hsz == 12) { w = u16(18); h = u16(20); planes = u16(22); bpp = u16(24); }
+    else { w = (int32_t)u32(18); h = (int32_t)u32(22); planes = u16(26); bpp = u16(28); comp = u32(30); }
+    if (planes != 1 || comp == 1 || comp == 2 || comp > 3 || (comp == 3 && bpp != 16 && bpp != 32)) return false;
+    const bool bottom_up = h > 0;
+    if (h < 0) h = -h;
+    if (w <= 0 || h == 0 || w > (1 << 24) || h > (1 << 24) || w * h > (1ll << 28)) return false;
+    uint32_t mask[3] = {0, 0, 0};                                    // R, G, B
+    if (bpp == 16 || bpp == 32) {
+        if (comp == 3) {
+            if (hsz == 12) return false;
+            // the masks follow the 40-byte core; for the 56-byte header the reference looks 16 bytes further (behind the header's
+            // own mask fields) -- kept, the aim being the reference's pixels
+            const size_t mo = hsz == 56 ? 70 : 54;
+            for (int c = 0; c < 3; c++) mask[c] = u32(mo + 4 * c);
+            if (hsz <= 56 && mask[0] == mask[1] && mask[1] == mask[2]) return false;
+        } else if (bpp == 16) { mask[0] = 31u << 10; mask[1] = 31u << 5; mask[2] = 31u; }
+        else { mask[0] = 0xffu << 16; mask[1] = 0xffu << 8; mask[2] = 0xffu; }
+        if (!mask[0] || !mask[1] || !mask[2]) return false;
+    }
+    const size_t head = 14 + (size_t)hsz + ((hsz <= 56 && comp == 3) ? 12 : 0);     // palette (if any) starts here
+    if (offs < head || offs > buf.size()) return false;
+    size_t row_bytes;
+    uint8_t pal[256][3];
+    if (bpp == 1 || bpp == 4 || bpp == 8) {
+        // (OS/2 header: the reference sizes the palette four entries short and reads uninitialised memory for the rest; every entry
+        // it does load is the one read here)
+        const size_t entry = hsz == 12 ? 3 : 4, n = (offs - head) / entry;
+        if (n == 0 || n > 256 || head + n * entry > buf.size()) return false;
+        memset(pal, 0, sizeof pal);
+        for (size_t i = 0; i < n; i++) { pal[i][2] = buf[head + i * entry]; pal[i][1] = buf[head + i * entry + 1]; pal[i][0] = buf[head + i * entry + 2]; }
+        row_bytes = ((size_t)w * bpp + 7) / 8;
+    } else if (bpp == 16 || bpp == 24 || bpp == 32) {
+        if (offs - head > 1024) return false;
+        row_bytes = (size_t)w * (bpp / 8);
+    } else return false;
+    const size_t stride = (row_bytes + 3) & ~(size_t)3;
+    if (offs + stride * (size_t)(h - 1) + row_bytes > buf.size()) return false;
+    int shift[3] = {0, 0, 0}, bits[3] = {0, 0, 0};
+    for (int c = 0; c < 3 && (bpp == 16 || bpp == 32); c++) {
+        int hi = 31;
+        while (!(mask[c] >> hi)) hi--;
+        shift[c] = hi - 7;                                           // brings the field's top bit to bit 7
+        bits[c] = __builtin_popcount(mask[c]);
+        if (bits[c] > 8) return false;
+    }
+    auto widen = [](uint32_t v, int n) -> uint8_t {                   // n-bit value -> 8 bits by bit replication
+        if (n == 0) return 0;
+        uint32_t r = 0;
+        for (int have = 0; have < 8; have += n) r = (r << n) | v;
+        const int extra = ((8 + n - 1) / n) * n - 8;
+        return (uint8_t)(r >> extra);
+    };
+    rgb.resize((size_t)w * h * 3);
+    for (int64_t y = 0; y < h; y++) {
+        const uint8_t* row = &buf[offs + stride * (size_t)(bottom_up ? h - 1 - y : y)];
+        uint8_t* out = &rgb[(size_t)y * w * 3];
+        for (int64_t x = 0; x < w; x++, out += 3) {
+            if (bpp <= 8) {
+                const int idx = bpp == 8 ? row[x] : (bpp == 4 ? (row[x >> 1] >> ((~x & 1) * 4)) & 15 : (row[x >> 3] >> (7 - (x & 7))) & 1);
+                out[0] = pal[idx][0]; out[1] = pal[idx][1]; out[2] = pal[idx][2];
+            } else if (bpp == 24 || (bpp == 32 && mask[0] == 0xff0000u && mask[1] == 0xff00u && mask[2] == 0xffu)) {
+                const uint8_t* px = row + x * (bpp / 8);
+                out[0] = px[2]; out[1] = px[1]; out[2] = px[0];
+            } else {
+                const uint8_t* px = row + x * (bpp / 8);
+                const uint32_t v = bpp == 16 ? (uint32_t)px[0] | ((uint32_t)px[1] << 8) : (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16) | ((uint32_t)px[3] << 24);
+                for (int c = 0; c < 3; c++) {
+                    uint32_t f = v & mask[c];
+                    f = shift[c] < 0 ? f << -shift[c] : f >> shift[c];
+                    out[c] = widen(f >> (8 - bits[c]), bits[c]);
+                }
+            }
+        }
+    }
+    nx = (int)w; ny = (int)h;
+    return true;
+}
+
 static bool load_image_file_impl(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny);
 bool load_image_file(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny) {
     try {
@@ -521,7 +609,7 @@ static bool load_image_file_impl(const char* fname, std::vector<uint8_t>& rgb, i
     if (got != buf.size() || buf.empty()) return false;
     if (buf.size() >= 8 && buf[0] == 0x89 && buf[1] == 'P' && buf[2] == 'N' && buf[3] == 'G') return decode_png(buf, rgb, nx, ny);
     if (buf.size() >= 4 && buf[0] == 0xFF && buf[1] == 0xD8) return decode_jpeg(buf.data(), buf.size(), rgb, nx, ny);
-    if (buf.size() >= 2 && buf[0] == 'P' && buf[1] == '6') {
+    if (buf.size() >= 2 && buf[0] == 'P' && (buf[1] == '6' || buf[1] == '5')) {       // binary PPM / PGM, samples of at most 8 bits, no scaling
         size_t p = 2;
         int vals[3], got = 0;
         while (got < 3 && p < buf.size()) {
@@ -532,30 +620,20 @@ static bool load_image_file_impl(const char* fname, std::vector<uint8_t>& rgb, i
             if (!any) return false;
             vals[got++] = v;
         }
-        if (got < 3 || vals[2] != 255) return false;
+        if (got < 3 || vals[2] < 1 || vals[2] > 255) return false;      // (16-bit PNM: the reference returns the LOW byte of every sample; refused here)
         p++;   // single whitespace after maxval
         nx = vals[0]; ny = vals[1];
-        const size_t need = (size_t)nx * ny * 3;
-        if (nx <= 0 || ny <= 0 || p + need > buf.size()) return false;
-        rgb.assign(buf.begin() + p, buf.begin() + p + need);
-        return true;
-    }
-    if (buf.size() >= 54 && buf[0] == 'B' && buf[1] == 'M') {
-        uint32_t offs; int32_t w, h; uint16_t bpp; uint32_t comp;
-        memcpy(&offs, &buf[10], 4); memcpy(&w, &buf[18], 4); memcpy(&h, &buf[22], 4); memcpy(&bpp, &buf[28], 2); memcpy(&comp, &buf[30], 4);
-        if (bpp != 24 || comp != 0 || w <= 0 || h == 0) return false;
-        const bool flip = h > 0;
-        const int hh = h > 0 ? h : -h;
-        const size_t stride = ((size_t)w * 3 + 3) & ~(size_t)3;
-        if (offs + stride * hh > buf.size()) return false;
-        nx = w; ny = hh;
-        rgb.resize((size_t)w * hh * 3);
-        for (int y = 0; y < hh; y++) {
-            const uint8_t* row = &buf[offs + stride * (flip ? (hh - 1 - y) : y)];
-            for (int x = 0; x < w; x++) { rgb[3 * ((size_t)y * w + x) + 0] = row[3 * x + 2]; rgb[3 * ((size_t)y * w + x) + 1] = row[3 * x + 1]; rgb[3 * ((size_t)y * w + x) + 2] = row[3 * x + 0]; }
+        if (nx <= 0 || ny <= 0 || (uint64_t)nx * (uint64_t)ny > (1ull << 28)) return false;
+        const size_t ch = buf[1] == '6' ? 3 : 1, need = (size_t)nx * ny * ch;
+        if (p + need > buf.size()) return false;
+        if (ch == 3) rgb.assign(buf.begin() + p, buf.begin() + p + need);
+        else {
+            rgb.resize(need * 3);
+            for (size_t i = 0; i < need; i++) rgb[3 * i] = rgb[3 * i + 1] = rgb[3 * i + 2] = buf[p + i];
         }
         return true;
     }
+    if (buf.size() >= 26 && buf[0] == 'B' && buf[1] == 'M') return decode_bmp(buf, rgb, nx, ny);
     return false;
 }
 

@@ -279,6 +279,84 @@ def test_png_every_colour_type_depth_and_interlace(prod, tmp_path):
     assert n == 6 * 2 * 15
 
 
+def _bmp(w, h, bpp, row_fn, hsz=40, comp=0, masks=None, palette=None, topdown=False):
+    """BMP writer for the decoder tests: OS/2 (12) and Windows (40 / 108 / 124) headers, palettes, BI_BITFIELDS, both row orders."""
+    import struct
+    pal = b"" if palette is None else b"".join(bytes([p[2], p[1], p[0]]) + (b"" if hsz == 12 else b"\0") for p in palette)
+    extra = b""
+    if hsz == 12:
+        hdr = struct.pack("<IHHHH", 12, w, h, 1, bpp)
+    else:
+        hdr = struct.pack("<IiiHHIIiiII", hsz, w, -h if topdown else h, 1, bpp, comp, 0, 2835, 2835, 0, 0)
+        if hsz == 40 and comp == 3:
+            extra = struct.pack("<III", *masks)
+        if hsz >= 108:
+            m = masks or (0, 0, 0)
+            hdr += struct.pack("<IIII", m[0], m[1], m[2], 0) + b"\0" * (hsz - 56)
+    stride = ((w * bpp + 31) // 32) * 4
+    rows = [row_fn(y) for y in (range(h) if topdown else range(h - 1, -1, -1))]
+    offs = 14 + len(hdr) + len(extra) + len(pal)
+    return b"BM" + struct.pack("<IHHI", offs + stride * h, 0, 0, offs) + hdr + extra + pal + b"".join(r + b"\0" * (stride - len(r)) for r in rows)
+
+
+def _field(v, mask):
+    """BI_BITFIELDS: the masked field, widened to 8 bits by repeating its bits (what stb_image does)."""
+    n = bin(mask).count("1")
+    lo = (mask & -mask).bit_length() - 1
+    f = (int(v) & mask) >> lo
+    bits = format(f, "0%db" % n) * 8
+    return int(bits[:8], 2)
+
+
+def test_bmp_and_pnm_variants(prod, tmp_path):
+    """clip_image_load_from_file on BMP (palettes of 1/4/8 bits, 16-bit 555 / 565 / 444, 24-bit, 32-bit, V3/V4/V5 and OS/2 headers,
+    top-down rows) and binary PGM / PPM: against the rule computed here and, when oracle/_ref is built, the reference library."""
+    rng = np.random.default_rng(21)
+    ref = bd.ClipLib(ref_run.REF_LIB) if ref_run.available() else None
+    p = str(tmp_path / "t.bin")
+
+    def check(data, want, vs_ref=True):
+        open(p, "wb").write(data)
+        got = _load_file(prod, p)
+        assert got is not None, prod.last_error()
+        assert np.array_equal(got, want)
+        if ref is not None and vs_ref:
+            assert np.array_equal(got, _load_file(ref, p))
+
+    for (w, h) in [(1, 1), (5, 3), (13, 7), (33, 10)]:
+        for topdown in (False, True):
+            px = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+            check(_bmp(w, h, 24, lambda y: bytes(px[y, :, 2::-1].reshape(-1)), topdown=topdown), px[..., :3])
+            for hsz in (40, 108, 124):
+                check(_bmp(w, h, 32, lambda y: bytes(px[y][:, [2, 1, 0, 3]].reshape(-1)), hsz=hsz, topdown=topdown), px[..., :3])
+                v16 = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+                for comp, masks in ((0, (0x7C00, 0x03E0, 0x001F)), (3, (0xF800, 0x07E0, 0x001F)), (3, (0x0F00, 0x00F0, 0x000F))):
+                    want = np.array([[[_field(v, m) for m in masks] for v in r] for r in v16], np.uint8)
+                    check(_bmp(w, h, 16, lambda y: v16[y].astype("<u2").tobytes(), hsz=hsz, comp=comp, masks=masks, topdown=topdown), want)
+            for bpp in (1, 4, 8):
+                pal = rng.integers(0, 256, (1 << bpp, 3), dtype=np.uint8)
+                idx = rng.integers(0, 1 << bpp, (h, w))
+
+                def row(y):
+                    bits = "".join(format(int(v), "0%db" % bpp) for v in idx[y])
+                    bits += "0" * (-len(bits) % 8)
+                    return bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8))
+                check(_bmp(w, h, bpp, row, palette=pal, topdown=topdown), pal[idx])
+                if not topdown:     # OS/2 header: the reference reads part of the palette from uninitialised memory -- rule only
+                    check(_bmp(w, h, bpp, row, hsz=12, palette=pal), pal[idx], vs_ref=False)
+    g = rng.integers(0, 256, (5, 7), dtype=np.uint8)
+    c = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    check(b"P5\n# comment\n7 5\n255\n" + g.tobytes(), np.repeat(g[..., None], 3, -1))
+    check(b"P5 7 5 15\n" + (g & 15).tobytes(), np.repeat((g & 15)[..., None], 3, -1))
+    check(b"P6\n#a\n7\n#b\n5\n255\n" + c.tobytes(), c)
+    open(p, "wb").write(b"P6 7 5 65535\n" + bytes(7 * 5 * 6))
+    assert _load_file(prod, p) is None
+    rle = bytearray(_bmp(4, 4, 8, lambda y: bytes(4), palette=rng.integers(0, 256, (256, 3), dtype=np.uint8)))
+    rle[30] = 1                                                    # BI_RLE8: refused, as in the reference
+    open(p, "wb").write(bytes(rle))
+    assert _load_file(prod, p) is None
+
+
 JPEG_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jpeg")
 
 
