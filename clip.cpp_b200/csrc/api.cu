@@ -676,7 +676,7 @@ bool clip_image_load_from_file(const char* fname, struct clip_image_u8* img) {
     int nx = 0, ny = 0;
     if (!load_image_file(fname, rgb, nx, ny)) {
         set_err(std::string("clip_image_load_from_file: cannot decode '") + fname + "': supported formats are JPEG (Huffman baseline / progressive, 8-bit), PNG, "
-                "BMP (uncompressed) and binary PGM / PPM; GIF / TGA / PSD / HDR and arithmetic-coded or 12-bit JPEG are not decoded by this library -- convert first");
+                "BMP (uncompressed), GIF (first frame) and binary PGM / PPM; TGA / PSD / HDR / PIC and arithmetic-coded or 12-bit JPEG are not decoded by this library -- convert first");
         return false;
     }
     img->nx = nx; img->ny = ny; img->size = rgb.size();

@@ -201,6 +201,116 @@ static bool decode_bmp(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rg
     return true;
 }
 
+// GIF, first frame only, as stb_image composes it for a 3-channel request: the canvas starts black; every pixel of the first image
+// whose colour is not the transparent index is painted; canvas pixels the image does not cover take the background colour when the
+// background index is non-zero; transparent pixels stay black.  GIF87a / GIF89a, global or local colour table, interlaced rows.
+static bool decode_gif(const std::vector<uint8_t>& buf, std::vector<uint8_t>& rgb, int& nx, int& ny) {
+    size_t p = 0;
+    bool eof = false;
+    auto u8 = [&]() -> int { if (p < buf.size()) return buf[p++]; eof = true; return 0; };
+    auto u16 = [&]() -> int { const int lo = u8(); return lo | (u8() << 8); };
+    if (buf.size() < 13 || memcmp(buf.data(), "GIF8", 4) != 0 || (buf[4] != '7' && buf[4] != '9') || buf[5] != 'a') return false;
+    p = 6;
+    const int W = u16(), H = u16(), flags = u8(), bgindex = u8();
+    u8();                                                              // pixel aspect ratio
+    if (W <= 0 || H <= 0 || (int64_t)W * H > (1ll << 28)) return false;
+    uint8_t gpal[256][3], lpal[256][3];
+    memset(gpal, 0, sizeof gpal);
+    if (flags & 0x80)
+        for (int i = 0, n = 2 << (flags & 7); i < n; i++) { gpal[i][0] = (uint8_t)u8(); gpal[i][1] = (uint8_t)u8(); gpal[i][2] = (uint8_t)u8(); }
+    int transparent = -1;                                              // index made transparent by the last graphic control extension
+    for (;;) {
+        if (eof) return false;
+        const int tag = u8();
+        if (tag == 0x21) {                                             // extension
+            const int ext = u8();
+            int len;
+            if (ext == 0xF9) {
+                len = u8();
+                if (len == 4) {
+                    const int eflags = u8();
+                    u16();                                             // delay
+                    const int t = u8();
+                    transparent = (eflags & 1) ? t : -1;
+                } else { p += (size_t)len; continue; }
+            }
+            while ((len = u8()) != 0 && !eof) p += (size_t)len;       // sub-blocks
+            continue;
+        }
+        if (tag != 0x2C) return false;                                 // 0x3B (trailer) before any image, or garbage
+        const int x0 = u16(), y0 = u16(), w = u16(), h = u16(), lflags = u8();
+        if (x0 + w > W || y0 + h > H) return false;
+        const uint8_t(*pal)[3];
+        if (lflags & 0x80) {
+            memset(lpal, 0, sizeof lpal);
+            for (int i = 0, n = 2 << (lflags & 7); i < n; i++) { lpal[i][0] = (uint8_t)u8(); lpal[i][1] = (uint8_t)u8(); lpal[i][2] = (uint8_t)u8(); }
+            pal = lpal;
+        } else if (flags & 0x80) pal = gpal;
+        else return false;
+        rgb.assign((size_t)W * H * 3, 0);
+        std::vector<uint8_t> visited((size_t)W * H, 0);
+        // pixel cursor over the image rectangle; interlaced files deliver rows 0, 8, 16.. then 4, 12.. then 2, 6.. then 1, 3..
+        int cx = 0, cy = 0, pass = (lflags & 0x40) ? 3 : 0, step = (lflags & 0x40) ? 8 : 1;
+        bool full = (w == 0 || h == 0);
+        auto put = [&](int idx) {
+            if (full) return;
+            const size_t at = (size_t)(y0 + cy) * W + (x0 + cx);
+            visited[at] = 1;
+            if (idx != transparent) { rgb[3 * at] = pal[idx][0]; rgb[3 * at + 1] = pal[idx][1]; rgb[3 * at + 2] = pal[idx][2]; }
+            if (++cx < w) return;
+            cx = 0;
+            cy += step;
+            while (cy >= h && pass > 0) { step = 1 << pass; cy = step >> 1; pass--; }
+            if (cy >= h) full = true;
+        };
+        // LZW (variable code width, LSB first, data in sub-blocks)
+        const int min_bits = u8();
+        if (min_bits > 12) return false;
+        const int clear = 1 << min_bits;
+        struct Code { int16_t prefix; uint8_t first, suffix; };
+        std::vector<Code> codes(8192);
+        for (int i = 0; i < clear; i++) codes[i] = {-1, (uint8_t)i, (uint8_t)i};
+        std::vector<uint8_t> stack(8192 + 1);
+        int width = min_bits + 1, mask = (1 << width) - 1, avail = clear + 2, old = -1, block = 0, nbits = 0;
+        uint32_t acc = 0;
+        bool seen_clear = false;
+        for (;;) {
+            if (nbits < width) {
+                if (block == 0) { block = u8(); if (block == 0) break; }
+                block--;
+                acc |= (uint32_t)u8() << nbits;
+                nbits += 8;
+                if (eof) break;
+                continue;
+            }
+            const int code = (int)(acc & (uint32_t)mask);
+            acc >>= width;
+            nbits -= width;
+            if (code == clear) { width = min_bits + 1; mask = (1 << width) - 1; avail = clear + 2; old = -1; seen_clear = true; continue; }
+            if (code == clear + 1) break;                              // end of information
+            if (code > avail || !seen_clear) return false;
+            if (old >= 0) {
+                if (avail >= 8192) return false;
+                Code& c = codes[avail++];
+                c.prefix = (int16_t)old;
+                c.first = codes[old].first;
+                c.suffix = code == avail - 1 ? c.first : codes[code].first;
+            } else if (code == avail) return false;
+            int n = 0;
+            for (int c = code; c >= 0 && n < 8192; c = codes[c].prefix) stack[n++] = codes[c].suffix;
+            while (n > 0) put(stack[--n]);
+            if ((avail & mask) == 0 && avail <= 0x0FFF) { width++; mask = (1 << width) - 1; }
+            old = code;
+        }
+        // (the reference copies its B,G,R-ordered table entry straight into the R,G,B canvas here: background red and blue arrive swapped)
+        if (bgindex > 0)
+            for (size_t i = 0; i < visited.size(); i++)
+                if (!visited[i]) { rgb[3 * i] = gpal[bgindex][2]; rgb[3 * i + 1] = gpal[bgindex][1]; rgb[3 * i + 2] = gpal[bgindex][0]; }
+        nx = W; ny = H;
+        return true;
+    }
+}
+
 static bool load_image_file_impl(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny);
 bool load_image_file(const char* fname, std::vector<uint8_t>& rgb, int& nx, int& ny) {
     try {
@@ -249,6 +359,7 @@ static bool load_image_file_impl(const char* fname, std::vector<uint8_t>& rgb, i
         return true;
     }
     if (buf.size() >= 26 && buf[0] == 'B' && buf[1] == 'M') return decode_bmp(buf, rgb, nx, ny);
+    if (buf.size() >= 13 && buf[0] == 'G' && buf[1] == 'I' && buf[2] == 'F') return decode_gif(buf, rgb, nx, ny);
     return false;
 }
 

@@ -113,9 +113,9 @@ void clip_image_f32_free(struct clip_image_f32 * res);
 
 /* clip.h:87, clip.cpp:709-726 -- the reference decodes with stb_image; this library has its own decoders for JPEG (Huffman baseline and
  * progressive, 8-bit, grey / YCbCr / RGB / CMYK / YCCK, any integer sampling ratio, restart intervals), PNG (every colour type and bit
- * depth, plain or Adam7-interlaced), BMP (palettes, 16 / 24 / 32 bits, no RLE) and binary PGM / PPM.  Each returns the same 3-channel
+ * depth, plain or Adam7-interlaced), BMP (palettes, 16 / 24 / 32 bits, no RLE), GIF (first frame) and binary PGM / PPM.  Each returns the same 3-channel
  * pixels as stb_image, byte for byte (JPEG included: the inverse DCT, chroma up-sampling and colour conversion follow stb_image's
- * integer arithmetic; tests/golden/jpeg).  GIF / TGA / PSD / HDR and arithmetic-coded or 12-bit JPEG return false with an explicit
+ * integer arithmetic; tests/golden/jpeg).  TGA / PSD / HDR / PIC and arithmetic-coded or 12-bit JPEG return false with an explicit
  * message in clip_b200_last_error. */
 bool clip_image_load_from_file(const char * fname, struct clip_image_u8 * img);
 

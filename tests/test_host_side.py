@@ -131,9 +131,9 @@ def _load_file(lib, path):
     return np.ctypeslib.as_array(im.data, shape=(im.ny, im.nx, 3)).copy()
 
 
-def test_png_decode_matches_pil_and_rejects_gif(prod, tmp_path):
+def test_png_decode_matches_pil_and_rejects_unknown_formats(prod, tmp_path):
     """clip_image_load_from_file (clip.cpp:709-726): PNG of every colour type decodes to the 3-channel pixels stb_image / PIL give;
-    a format without a decoder here (GIF) is refused with an explicit message instead of garbage."""
+    a format without a decoder here (TIFF) is refused with an explicit message instead of garbage."""
     Image = pytest.importorskip("PIL.Image")
     rng = np.random.default_rng(0)
     rgb = rng.integers(0, 256, (37, 53, 3), dtype=np.uint8)
@@ -146,9 +146,9 @@ def test_png_decode_matches_pil_and_rejects_gif(prod, tmp_path):
         got = _load_file(prod, p)
         assert got is not None, (name, prod.last_error())
         assert np.array_equal(got, np.array(Image.open(p).convert("RGB"))), name
-    g = str(tmp_path / "x.gif")
+    g = str(tmp_path / "x.tif")
     Image.fromarray(rgb).save(g)
-    assert _load_file(prod, g) is None and b"GIF" in prod.lib.clip_b200_last_error()
+    assert _load_file(prod, g) is None and b"supported formats" in prod.lib.clip_b200_last_error()
 
 
 @pytest.mark.skipif(not ref_run.available(), reason="oracle/_ref not built")
@@ -354,6 +354,120 @@ def test_bmp_and_pnm_variants(prod, tmp_path):
     rle = bytearray(_bmp(4, 4, 8, lambda y: bytes(4), palette=rng.integers(0, 256, (256, 3), dtype=np.uint8)))
     rle[30] = 1                                                    # BI_RLE8: refused, as in the reference
     open(p, "wb").write(bytes(rle))
+    assert _load_file(prod, p) is None
+
+
+def _gif_lzw(indices, min_bits, grow=True):
+    """GIF LZW.  grow=False: a clear code before the code width would change (fixed-width stream); grow=True: a real dictionary coder."""
+    clear, eoi = 1 << min_bits, (1 << min_bits) + 1
+    out, state = bytearray(), [0, 0]
+
+    def emit(code, width):
+        state[0] |= code << state[1]
+        state[1] += width
+        while state[1] >= 8:
+            out.append(state[0] & 255)
+            state[0] >>= 8
+            state[1] -= 8
+    width = min_bits + 1
+    emit(clear, width)
+    if not grow:
+        for i, v in enumerate(indices):
+            if i and i % (clear - 2) == 0:
+                emit(clear, width)
+            emit(int(v), width)
+    else:
+        table, nxt, cur = {(i,): i for i in range(clear)}, eoi + 1, ()
+        for v in indices:
+            k = cur + (int(v),)
+            if k in table:
+                cur = k
+                continue
+            emit(table[cur], width)
+            table[k] = nxt
+            nxt += 1
+            if nxt > (1 << width) and width < 12:
+                width += 1
+            if nxt >= 4095:
+                emit(clear, width)
+                table, nxt, width = {(i,): i for i in range(clear)}, eoi + 1, min_bits + 1
+            cur = (int(v),)
+        if cur:
+            emit(table[cur], width)
+    emit(eoi, width)
+    if state[1]:
+        out.append(state[0] & 255)
+    return bytes([min_bits]) + b"".join(bytes([len(out[i:i + 255])]) + bytes(out[i:i + 255]) for i in range(0, len(out), 255)) + b"\0"
+
+
+def _gif(W, H, gpal, frame, x0=0, y0=0, bg=0, transparent=None, interlace=False, lpal=None, grow=True):
+    import struct
+    h, w = frame.shape
+
+    def table(p):
+        n = max(1, int(np.ceil(np.log2(max(len(p), 2)))))
+        return n, bytes(np.asarray(p, np.uint8).reshape(-1)) + b"\0" * (3 * ((1 << n) - len(p)))
+    d = b"GIF89a"
+    if gpal is not None:
+        n, t = table(gpal)
+        d += struct.pack("<HHBBB", W, H, 0x80 | (n - 1), bg, 0) + t
+    else:
+        d += struct.pack("<HHBBB", W, H, 0, bg, 0)
+    d += b"\x21\xFE\x05hello\0"
+    if transparent is not None:
+        d += b"\x21\xF9\x04" + bytes([1, 0, 0, transparent]) + b"\0"
+    rows = list(range(h))
+    if interlace:
+        rows = list(range(0, h, 8)) + list(range(4, h, 8)) + list(range(2, h, 4)) + list(range(1, h, 2))
+    ncol = len(lpal) if lpal is not None else len(gpal)
+    lf = 0x40 if interlace else 0
+    if lpal is not None:
+        n, t = table(lpal)
+        d += b"\x2C" + struct.pack("<HHHHB", x0, y0, w, h, lf | 0x80 | (n - 1)) + t
+    else:
+        d += b"\x2C" + struct.pack("<HHHHB", x0, y0, w, h, lf)
+    return d + _gif_lzw(frame[rows].reshape(-1), max(2, int(np.ceil(np.log2(max(ncol, 2))))), grow) + b"\x3B"
+
+
+def test_gif_first_frame(prod, tmp_path):
+    """clip_image_load_from_file on GIF: the first frame as stb_image composes it (transparent pixels black, uncovered canvas = background
+    colour when its index is non-zero -- with red and blue swapped, a quirk of the reference that is kept), interlaced rows, local
+    colour tables, both LZW styles; against the rule computed here and, when oracle/_ref is built, the reference library."""
+    rng = np.random.default_rng(31)
+    ref = bd.ClipLib(ref_run.REF_LIB) if ref_run.available() else None
+    p = str(tmp_path / "t.gif")
+
+    def check(data, want):
+        open(p, "wb").write(data)
+        got = _load_file(prod, p)
+        assert got is not None, prod.last_error()
+        assert np.array_equal(got, want)
+        if ref is not None:
+            assert np.array_equal(got, _load_file(ref, p))
+
+    for (W, H) in [(1, 1), (7, 5), (33, 21), (120, 90)]:
+        for ncol in (2, 16, 200, 256):
+            pal = rng.integers(0, 256, (ncol, 3), dtype=np.uint8)
+            lp = rng.integers(0, 256, (ncol, 3), dtype=np.uint8)
+            fr = rng.integers(0, ncol, (H, W))
+            smooth = (np.add.outer(np.arange(H), np.arange(W)) // 3) % ncol
+            for grow in (False, True):
+                for il in (False, True):
+                    check(_gif(W, H, pal, fr, interlace=il, grow=grow), pal[fr])
+                    check(_gif(W, H, pal, smooth, interlace=il, grow=grow), pal[smooth])
+            want = pal[fr].copy()
+            want[fr == 1] = 0
+            check(_gif(W, H, pal, fr, transparent=1), want)
+            check(_gif(W, H, None, fr, lpal=lp), lp[fr])
+            if W > 4 and H > 3:
+                sub = fr[1:H - 1, 2:W - 1]
+                for bg in (0, ncol - 1):
+                    want = np.zeros((H, W, 3), np.uint8)
+                    if bg:
+                        want[:] = pal[bg][::-1]
+                    want[1:H - 1, 2:W - 1] = pal[sub]
+                    check(_gif(W, H, pal, sub, x0=2, y0=1, bg=bg, interlace=True), want)
+    open(p, "wb").write(b"GIF89a" + bytes(7) + b"\x3B")
     assert _load_file(prod, p) is None
 
 
