@@ -73,6 +73,23 @@ def main():
             tr = min(tr, (time.perf_counter() - t0) * 1e3)
         print("| %dx%d | %.1f ms | %.1f ms | %s |" % (w, h, tp, tr, np.array_equal(out.ravel(), np.asarray(r).ravel())))
 
+    # file quantizer (clip_model_quantize, clip.cpp:1661-1844): single-threaded in both libraries, output files byte-identical
+    import synth_gguf as sg
+    print("\n| clip_model_quantize, ViT-L/14 f16 (857 MB) -> | this library | reference | identical file |\n|---|---|---|---|")
+    src = sg.model_path("vit-l14", 1234, "f16")
+    if not os.path.exists(src):
+        sg.write_model(src, sg.GEOMETRIES["vit-l14"], 1234, 1)
+    if True:
+        for it, name in ((2, "q4_0"), (8, "q8_0")):
+            t0 = time.perf_counter()
+            assert prod.quantize(src, "/tmp/host_timing_p.gguf", it)
+            tp = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            assert ref.quantize(src, "/tmp/host_timing_r.gguf", it)
+            tr = time.perf_counter() - t0
+            same = open("/tmp/host_timing_p.gguf", "rb").read() == open("/tmp/host_timing_r.gguf", "rb").read()
+            print("| %s | %.1f s | %.1f s | %s |" % (name, tp, tr, "yes" if same else "NO"))
+
 
 if __name__ == "__main__":
     main()
