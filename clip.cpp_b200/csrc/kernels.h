@@ -7,7 +7,8 @@ namespace cb {
 
 // K2 LayerNorm: y16[r, :] = ((x[r*in_stride ...] - mean) * rstd) * gamma + beta   (reference: ggml.c:10796-10845,
 // affine clip.cpp:1071-1074).  x fp32, row r starts at x + r*in_stride.  One warp per row.
-// If delta16 != NULL the kernel first applies the pending residual branch: x[r,:] += delta16[r,:] (written back in fp32).
+// If delta16 != NULL the kernel first applies a pending residual branch: x[r,:] += delta16[r,:] (written back in fp32); the model
+// schedule passes NULL (round 2: the GEMM epilogues add into x).
 void launch_layernorm(float* x, size_t in_stride, int rows, int h, float eps, const float* gamma, const float* beta,
                       const void* delta16, void* y16, int bf16, cudaStream_t st);
 
