@@ -10,9 +10,9 @@
 //   * colour: 20-bit fixed point with 12-bit coefficients, the Cb term of green truncated to its upper 16 bits.
 // tests/test_host_side.py checks the result byte for byte against the reference's loader on tests/golden/jpeg/*.jpg (fixtures made by
 // tests/golden/make_jpeg_golden.py) and, when /root/reference is there, on the reference's own two sample JPEGs.
-// Speed (8 host cores, vs the reference's stb_image with its SSE2 kernels): 600x500 progressive 1.8 ms vs 2.3 ms; 4000x3000 baseline
-// 132 ms vs 147 ms, progressive 181 ms vs 240 ms -- single lookup for short AC codes, lane-parallel integer IDCT, IDCT / colour rows on
-// up to 8 threads from a megapixel up.
+// Speed (profiles/r02_host_side.md; vs the reference's stb_image with its SSE2 kernels): 600x500 baseline 2.3 ms vs 2.7 ms, progressive
+// 3.8 ms vs 5.0 ms; 4000x3000 baseline 126 ms vs 140 ms, progressive 170 ms vs 235 ms -- single lookup for short AC codes, AVX2 integer
+// IDCT and colour rows (portable loops otherwise, same bytes), IDCT / colour rows on up to 8 threads from a megapixel up.
 // Not supported (load fails, as it does in the reference): arithmetic coding, lossless / hierarchical modes, 12-bit samples.
 #include <stdint.h>
 #include <stdlib.h>
@@ -22,6 +22,10 @@
 #include <vector>
 
 #include "host_ops.h"
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
 
 namespace cb {
 namespace {
@@ -185,7 +189,7 @@ inline uint8_t clamp_u8(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x
 
 // de-quantised coefficients (row-major) -> 8x8 samples.  Column pass: 10 of the 12 fraction bits dropped (2 guard bits stay); row
 // pass: 12 + 2 + 3 bits dropped with the +128 level shift folded into the rounding bias.
-CB_SIMD_CLONES void idct_block(const int16_t* d, uint8_t* out, int stride) {
+CB_SIMD_CLONES void idct_block_generic(const int16_t* d, uint8_t* out, int stride) {
     uint64_t ac = 0;                                            // DC-only blocks (most of a smooth image) are one flat value
     for (int i = 0; i < 16; i++) { uint64_t v; memcpy(&v, d + 4 * i, 8); ac |= i ? v : (v >> 16 << 16); }
     // (little-endian: d[0] is the low 16 bits of the first word)
@@ -204,6 +208,98 @@ CB_SIMD_CLONES void idct_block(const int16_t* d, uint8_t* out, int stride) {
     llm_pass8(a, b, 65536u + (128u << 17), 17);
     for (int r = 0; r < 8; r++)
         for (int c = 0; c < 8; c++) out[r * stride + c] = clamp_u8(b[c][r]);
+}
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#define CB_HAVE_AVX2_PATH 1
+#define CB_AVX2 __attribute__((target("avx2")))
+// The same two passes with the eight lanes in one 256-bit register per row and both transposes done with shuffles (the generic
+// version above spends more time transposing through memory than computing).  32-bit lanes wrap like the u32 arithmetic above.
+CB_AVX2 inline void llm_pass_avx2(__m256i v[8], int bias, int shift) {
+    const __m256i s0 = v[0], s1 = v[1], s2 = v[2], s3 = v[3], s4 = v[4], s5 = v[5], s6 = v[6], s7 = v[7];
+#define CB_MUL(x, c) _mm256_mullo_epi32((x), _mm256_set1_epi32(c))
+    const __m256i z = CB_MUL(_mm256_add_epi32(s2, s6), fx12(0.5411961f));
+    const __m256i c2 = _mm256_add_epi32(z, CB_MUL(s6, fx12(-1.847759065f)));
+    const __m256i c3 = _mm256_add_epi32(z, CB_MUL(s2, fx12(0.765366865f)));
+    const __m256i vb = _mm256_set1_epi32(bias);
+    const __m256i a = _mm256_add_epi32(_mm256_slli_epi32(_mm256_add_epi32(s0, s4), 12), vb);
+    const __m256i b = _mm256_add_epi32(_mm256_slli_epi32(_mm256_sub_epi32(s0, s4), 12), vb);
+    const __m256i e0 = _mm256_add_epi32(a, c3), e3 = _mm256_sub_epi32(a, c3), e1 = _mm256_add_epi32(b, c2), e2 = _mm256_sub_epi32(b, c2);
+    __m256i p3 = _mm256_add_epi32(s7, s3), p4 = _mm256_add_epi32(s5, s1), p1 = _mm256_add_epi32(s7, s1), p2 = _mm256_add_epi32(s5, s3);
+    const __m256i p5 = CB_MUL(_mm256_add_epi32(p3, p4), fx12(1.175875602f));
+    const __m256i t0 = CB_MUL(s7, fx12(0.298631336f)), t1 = CB_MUL(s5, fx12(2.053119869f));
+    const __m256i t2 = CB_MUL(s3, fx12(3.072711026f)), t3 = CB_MUL(s1, fx12(1.501321110f));
+    p1 = _mm256_add_epi32(p5, CB_MUL(p1, fx12(-0.899976223f)));
+    p2 = _mm256_add_epi32(p5, CB_MUL(p2, fx12(-2.562915447f)));
+    p3 = CB_MUL(p3, fx12(-1.961570560f));
+    p4 = CB_MUL(p4, fx12(-0.390180644f));
+#undef CB_MUL
+    const __m256i o0 = _mm256_add_epi32(t3, _mm256_add_epi32(p1, p4)), o1 = _mm256_add_epi32(t2, _mm256_add_epi32(p2, p3));
+    const __m256i o2 = _mm256_add_epi32(t1, _mm256_add_epi32(p2, p4)), o3 = _mm256_add_epi32(t0, _mm256_add_epi32(p1, p3));
+    const __m128i sh = _mm_cvtsi32_si128(shift);
+    v[0] = _mm256_sra_epi32(_mm256_add_epi32(e0, o0), sh); v[7] = _mm256_sra_epi32(_mm256_sub_epi32(e0, o0), sh);
+    v[1] = _mm256_sra_epi32(_mm256_add_epi32(e1, o1), sh); v[6] = _mm256_sra_epi32(_mm256_sub_epi32(e1, o1), sh);
+    v[2] = _mm256_sra_epi32(_mm256_add_epi32(e2, o2), sh); v[5] = _mm256_sra_epi32(_mm256_sub_epi32(e2, o2), sh);
+    v[3] = _mm256_sra_epi32(_mm256_add_epi32(e3, o3), sh); v[4] = _mm256_sra_epi32(_mm256_sub_epi32(e3, o3), sh);
+}
+
+CB_AVX2 inline void transpose8_avx2(__m256i v[8]) {
+    const __m256i t0 = _mm256_unpacklo_epi32(v[0], v[1]), t1 = _mm256_unpackhi_epi32(v[0], v[1]);
+    const __m256i t2 = _mm256_unpacklo_epi32(v[2], v[3]), t3 = _mm256_unpackhi_epi32(v[2], v[3]);
+    const __m256i t4 = _mm256_unpacklo_epi32(v[4], v[5]), t5 = _mm256_unpackhi_epi32(v[4], v[5]);
+    const __m256i t6 = _mm256_unpacklo_epi32(v[6], v[7]), t7 = _mm256_unpackhi_epi32(v[6], v[7]);
+    const __m256i u0 = _mm256_unpacklo_epi64(t0, t2), u1 = _mm256_unpackhi_epi64(t0, t2), u2 = _mm256_unpacklo_epi64(t1, t3), u3 = _mm256_unpackhi_epi64(t1, t3);
+    const __m256i u4 = _mm256_unpacklo_epi64(t4, t6), u5 = _mm256_unpackhi_epi64(t4, t6), u6 = _mm256_unpacklo_epi64(t5, t7), u7 = _mm256_unpackhi_epi64(t5, t7);
+    v[0] = _mm256_permute2x128_si256(u0, u4, 0x20); v[1] = _mm256_permute2x128_si256(u1, u5, 0x20);
+    v[2] = _mm256_permute2x128_si256(u2, u6, 0x20); v[3] = _mm256_permute2x128_si256(u3, u7, 0x20);
+    v[4] = _mm256_permute2x128_si256(u0, u4, 0x31); v[5] = _mm256_permute2x128_si256(u1, u5, 0x31);
+    v[6] = _mm256_permute2x128_si256(u2, u6, 0x31); v[7] = _mm256_permute2x128_si256(u3, u7, 0x31);
+}
+
+// eight int32 -> eight bytes, clamped to 0..255 (signed saturation to 16 bits, then unsigned saturation to 8)
+CB_AVX2 inline __m128i clamp8_avx2(__m256i x) {
+    const __m128i w = _mm_packs_epi32(_mm256_castsi256_si128(x), _mm256_extracti128_si256(x, 1));
+    return _mm_packus_epi16(w, w);
+}
+
+CB_AVX2 void idct_block_avx2(const int16_t* d, uint8_t* out, int stride) {
+    __m256i v[8];
+    __m128i any = _mm_setzero_si128();
+    for (int r = 0; r < 8; r++) {
+        const __m128i row = _mm_loadu_si128((const __m128i*)(d + 8 * r));
+        any = _mm_or_si128(any, r ? row : _mm_srli_si128(row, 2));   // every coefficient but d[0]
+        v[r] = _mm256_cvtepi16_epi32(row);
+    }
+    if (_mm_testz_si128(any, any)) {                                 // DC only: one flat value
+        const u32 col = (u32)((int32_t)d[0] * 4);
+        const int flat = (int32_t)(col * 4096u + 65536u + (128u << 17)) >> 17;
+        const __m128i f = _mm_set1_epi8((char)(flat < 0 ? 0 : (flat > 255 ? 255 : flat)));
+        for (int r = 0; r < 8; r++) _mm_storel_epi64((__m128i*)(out + r * stride), f);
+        return;
+    }
+    llm_pass_avx2(v, 512, 10);                                       // lanes = columns
+    transpose8_avx2(v);
+    llm_pass_avx2(v, 65536 + (128 << 17), 17);                       // lanes = rows
+    transpose8_avx2(v);
+    for (int r = 0; r < 8; r++) _mm_storel_epi64((__m128i*)(out + r * stride), clamp8_avx2(v[r]));
+}
+#endif
+
+// CLIP_B200_JPEG_SIMD=0 keeps the portable loops (the tests run both and expect the same bytes)
+bool use_avx2() {
+#ifdef CB_HAVE_AVX2_PATH
+    static const bool on = [] { const char* e = getenv("CLIP_B200_JPEG_SIMD"); return !(e && *e == '0') && __builtin_cpu_supports("avx2"); }();
+    return on;
+#else
+    return false;
+#endif
+}
+
+inline void idct_block(const int16_t* d, uint8_t* out, int stride) {
+#ifdef CB_HAVE_AVX2_PATH
+    if (use_avx2()) { idct_block_avx2(d, out, stride); return; }
+#endif
+    idct_block_generic(d, out, stride);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -258,8 +354,41 @@ inline uint8_t mul255(uint8_t x, uint8_t y) {
     return (uint8_t)((t + (t >> 8)) >> 8);
 }
 
-CB_SIMD_CLONES void ycc_row(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, uint8_t* out, int n) {
+CB_SIMD_CLONES void ycc_row_generic(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, uint8_t* out, int n) {
     for (int x = 0; x < n; x++) ycc_to_rgb(y[x], cb[x], cr[x], out + 3 * x);
+}
+
+#ifdef CB_HAVE_AVX2_PATH
+// eight pixels per step in 32-bit lanes (same arithmetic as ycc_to_rgb), bytes interleaved to R,G,B triples with two byte shuffles
+CB_AVX2 void ycc_row_avx2(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, uint8_t* out, int n) {
+    const __m256i k128 = _mm256_set1_epi32(128), half = _mm256_set1_epi32(1 << 19), hi16 = _mm256_set1_epi32((int)0xffff0000u);
+    const __m256i c_r = _mm256_set1_epi32(fx20(1.40200f)), c_g1 = _mm256_set1_epi32(-fx20(0.71414f)), c_g2 = _mm256_set1_epi32(-fx20(0.34414f)),
+                  c_b = _mm256_set1_epi32(fx20(1.77200f));
+    // from rg = r0 g0 r1 g1 .. r7 g7 and b = b0..b7: bytes 0..15 and 16..23 of the output
+    const __m128i m_rg0 = _mm_setr_epi8(0, 1, -1, 2, 3, -1, 4, 5, -1, 6, 7, -1, 8, 9, -1, 10), m_b0 = _mm_setr_epi8(-1, -1, 0, -1, -1, 1, -1, -1, 2, -1, -1, 3, -1, -1, 4, -1);
+    const __m128i m_rg1 = _mm_setr_epi8(11, -1, 12, 13, -1, 14, 15, -1, -1, -1, -1, -1, -1, -1, -1, -1), m_b1 = _mm_setr_epi8(-1, 5, -1, -1, 6, -1, -1, 7, -1, -1, -1, -1, -1, -1, -1, -1);
+    int x = 0;
+    for (; x + 8 <= n; x += 8) {
+        const __m256i yy = _mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i*)(y + x)));
+        const __m256i b_ = _mm256_sub_epi32(_mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i*)(cb + x))), k128);
+        const __m256i r_ = _mm256_sub_epi32(_mm256_cvtepu8_epi32(_mm_loadl_epi64((const __m128i*)(cr + x))), k128);
+        const __m256i yf = _mm256_add_epi32(_mm256_slli_epi32(yy, 20), half);
+        const __m256i r = _mm256_srai_epi32(_mm256_add_epi32(yf, _mm256_mullo_epi32(r_, c_r)), 20);
+        const __m256i g = _mm256_srai_epi32(_mm256_add_epi32(_mm256_add_epi32(yf, _mm256_mullo_epi32(r_, c_g1)), _mm256_and_si256(_mm256_mullo_epi32(b_, c_g2), hi16)), 20);
+        const __m256i b = _mm256_srai_epi32(_mm256_add_epi32(yf, _mm256_mullo_epi32(b_, c_b)), 20);
+        const __m128i rg = _mm_unpacklo_epi8(clamp8_avx2(r), clamp8_avx2(g)), bb = clamp8_avx2(b);
+        _mm_storeu_si128((__m128i*)(out + 3 * x), _mm_or_si128(_mm_shuffle_epi8(rg, m_rg0), _mm_shuffle_epi8(bb, m_b0)));
+        _mm_storel_epi64((__m128i*)(out + 3 * x + 16), _mm_or_si128(_mm_shuffle_epi8(rg, m_rg1), _mm_shuffle_epi8(bb, m_b1)));
+    }
+    for (; x < n; x++) ycc_to_rgb(y[x], cb[x], cr[x], out + 3 * x);
+}
+#endif
+
+inline void ycc_row(const uint8_t* y, const uint8_t* cb, const uint8_t* cr, uint8_t* out, int n) {
+#ifdef CB_HAVE_AVX2_PATH
+    if (use_avx2()) { ycc_row_avx2(y, cb, cr, out, n); return; }
+#endif
+    ycc_row_generic(y, cb, cr, out, n);
 }
 
 // [0, n) split into contiguous ranges over `threads` workers (the calling thread takes the first)

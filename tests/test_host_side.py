@@ -582,3 +582,14 @@ def test_reference_examples_link_unchanged_and_fail_loudly_without_a_gpu(prod):
     r = subprocess.run([bins[1], "-m", model, "--text", "apple", "--image", os.path.join(JPEG_GOLDEN, "pil_444_base.jpg")],
                        capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "no CUDA device" in (r.stdout + r.stderr), (r.returncode, r.stdout[-300:], r.stderr[-300:])
+
+
+def test_jpeg_portable_loops_give_the_same_bytes():
+    """csrc/jpeg.cpp picks AVX2 kernels for the inverse DCT and the colour rows at run time; CLIP_B200_JPEG_SIMD=0 keeps the portable
+    loops.  Both must produce the reference's pixels: the golden-hash test is run again in a process with the switch set."""
+    import subprocess
+    import sys
+    env = dict(os.environ, CLIP_B200_JPEG_SIMD="0")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-p", "no:cacheprovider", os.path.abspath(__file__) + "::test_jpeg_decode_matches_reference_golden"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout[-800:] + r.stderr[-400:]
