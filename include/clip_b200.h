@@ -231,7 +231,8 @@ bool   clip_b200_memcpy_d2h(const struct clip_ctx * ctx, void * h_dst, const voi
 bool   clip_b200_synchronize(const struct clip_ctx * ctx);
 void * clip_b200_get_stream(const struct clip_ctx * ctx);          /* the cudaStream_t every kernel is launched on */
 
-/* images (vision) / sequences (text) processed per pass through the layer stack; 0 keeps the current value */
+/* images (vision) / sequences (text) processed per pass through the layer stack; 0 keeps the current value.  Workspaces are sized
+ * once, at the first encode of a tower: a call after that is ignored for that tower. */
 void   clip_b200_set_micro_batch(const struct clip_ctx * ctx, int images, int sequences);
 
 /* measurement hooks */
